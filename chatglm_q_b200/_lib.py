@@ -1,0 +1,61 @@
+"""ctypes binding of the C-ABI library (include/cgq.h).  Fails loudly: there is no fallback."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libcgq.so"
+
+# every symbol include/cgq.h declares (tests check the library exports all of them)
+SYMBOLS = {
+    "cgq_version": (c_int, []),
+    "cgq_last_error": (c_char_p, []),
+    "cgq_workspace_bytes": (c_size_t, []),
+    "cgq_w4a16_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                               c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cgq_w4a16_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                  c_int]),
+    "cgq_w8a16_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                               c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "cgq_w8a16_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int]),
+    "cgq_w4_unpack_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "cgq_w4_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cgq_w4_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
+    "cgq_w8_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_void_p]),
+}
+
+IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC = 0, 1, 2, 3, 4
+
+_lib = None
+
+
+class CgqError(RuntimeError):
+    """A C-ABI call returned a non-zero status (message from cgq_last_error())."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m chatglm_q_b200.build` "
+            "(there is no CPU / PyTorch fallback for this path)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().cgq_last_error()
+        raise CgqError(f"cgq status {status}: {msg.decode() if msg else ''}")

@@ -1,0 +1,354 @@
+// int8 per-channel decode kernel (M <= 8 token rows): C[M,N] = A[M,K] · (Wq[N,K]^T * scale[N]).
+// Replaces _dynamic_quant_matmul_kernel (chatglm_q/int8/triton_ops.py:13-84) for decode.
+//
+// Same skeleton as gemv_w4.cu: persistent stream-K grid over (64-column tile, 128-k stage) units,
+// TMA ring (a [64 n x 128 k] byte tile with 128-byte swizzle + the activation slice), 4 consumer
+// warps.  The weight is K-contiguous, so a 16-byte run of one row is 8 ready-made (k, k+1) pairs:
+// int8 -> fp16 is `xor 0x80`, one PRMT against 0x64 (=> 1024+128+q) and one exact fp16 subtract.
+// Each warp owns 16 output columns (MMA rows) of the tile, so no cross-warp reduction is needed;
+// the per-channel scale multiplies the fp32 sum once in the epilogue (the reference rounds
+// q*scale to fp16 per element: ours is the more accurate side of the 1e-2 parity bar).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace cgq {
+namespace {
+
+constexpr int BN8 = 64;             // output columns (weight rows) per tile
+constexpr int CW = 4;               // consumer warps, 16 columns each
+constexpr int KSTAGE = 128;         // k bytes per stage (TMA inner box)
+constexpr int MMAX = 8;
+constexpr int A_STRIDE = KSTAGE * 2 + 32;
+constexpr int W_BYTES = BN8 * KSTAGE;
+constexpr int A_BYTES = MMAX * A_STRIDE;
+constexpr int RED_BYTES = MMAX * BN8 * 4;
+constexpr int kThreads = (CW + 1) * 32;
+
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// word = 4 consecutive int8 (k..k+3) -> (k,k+1) and (k+2,k+3) as packed T pairs, exact.
+template <typename T>
+struct Cvt8;
+template <>
+struct Cvt8<__half> {
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t& p01, uint32_t& p23) {
+    const uint32_t x = w ^ 0x80808080u;  // q + 128 as unsigned bytes
+    p01 = h2_sub(__byte_perm(x, 0x64646464u, 0x4140), 0x64806480u);  // (1024 + 128 + q) - 1152
+    p23 = h2_sub(__byte_perm(x, 0x64646464u, 0x4342), 0x64806480u);
+  }
+};
+template <>
+struct Cvt8<__nv_bfloat16> {
+  // bf16 has 8 significant bits: go through fp32 (2^23 + 128 + q) - (2^23 + 128), keep the top half
+  __device__ static __forceinline__ uint32_t one(uint32_t x, int sel) {
+    const float f = __uint_as_float(__byte_perm(x, 0x4B000000u, sel)) - 8388736.f;
+    return __float_as_uint(f);
+  }
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t& p01, uint32_t& p23) {
+    const uint32_t x = w ^ 0x80808080u;
+    const uint32_t f0 = one(x, 0x7440), f1 = one(x, 0x7441), f2 = one(x, 0x7442),
+                   f3 = one(x, 0x7443);
+    p01 = __byte_perm(f0, f1, 0x7632);  // high halves: (bf16(q0), bf16(q1))
+    p23 = __byte_perm(f2, f3, 0x7632);
+  }
+};
+
+struct Params {
+  const void* A;
+  int64_t lda;
+  const void* scale;
+  const void* bias;
+  void* C;
+  int64_t ldc;
+  int M, N, K;
+  int SPT, U, S;
+  int* counters;
+  float* partials;
+};
+
+__device__ __forceinline__ int unit_begin(int U, int P, int c) {
+  return static_cast<int>(static_cast<int64_t>(U) * c / P);
+}
+__device__ __forceinline__ int unit_owner(int U, int P, int u) {
+  return static_cast<int>((static_cast<int64_t>(u + 1) * P - 1) / U);
+}
+
+template <typename T, bool kM1>
+__global__ void __launch_bounds__(kThreads)
+    w8_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int S = p.S;
+  const uint32_t Wsm = base;
+  const uint32_t Asm = Wsm + S * W_BYTES;
+  const uint32_t off_red = S * (W_BYTES + A_BYTES);
+  float* red = reinterpret_cast<float*>(gen + off_red);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + RED_BYTES);
+  uint64_t* empty = full + S;
+  int* flag = reinterpret_cast<int*>(empty + S);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = gridDim.x, c = blockIdx.x;
+  const int u0 = unit_begin(p.U, P, c), u1 = unit_begin(p.U, P, c + 1);
+  const int n_units = u1 - u0;
+  const T* A = static_cast<const T*>(p.A);
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], CW);
+    }
+    ptx::fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < S * A_BYTES / 16; i += kThreads)
+    ptx::sts128(Asm + i * 16, make_uint4(0, 0, 0, 0));
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  ptx::pdl_launch_dependents();
+
+  if (warp == CW) {
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      auto issue_w = [&](int i, int slot) {
+        const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
+        const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
+        ptx::mbar_expect_tx(&full[slot], W_BYTES + p.M * kvalid * 2);
+        ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, ks * KSTAGE, tile * BN8, &full[slot], pol);
+      };
+      auto issue_a = [&](int i, int slot) {
+        const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
+        const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
+        uint8_t* dst = gen + S * W_BYTES + slot * A_BYTES;
+        for (int m = 0; m < p.M; ++m)
+          ptx::bulk_load_1d(dst + m * A_STRIDE, A + m * p.lda + ks * KSTAGE, kvalid * 2,
+                            &full[slot]);
+      };
+      const int prefill = min(n_units, S);
+      for (int i = 0; i < prefill; ++i) issue_w(i, i);
+      ptx::pdl_wait_prior_grid();
+      for (int i = 0; i < prefill; ++i) issue_a(i, i);
+      int slot = 0, phase = 1;
+      for (int i = prefill; i < n_units; ++i) {
+        ptx::mbar_wait(&empty[slot], phase ^ 1);
+        issue_w(i, slot);
+        issue_a(i, slot);
+        if (++slot == S) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  ptx::pdl_wait_prior_grid();
+  const int g = lane >> 2, tig = lane & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc2[4] = {0.f, 0.f, 0.f, 0.f};  // second chain: halves the HMMA dependency depth
+  const bool has_tok = kM1 ? (g == 0) : (g < p.M);
+  int slot = 0, phase = 0;
+  int tile = u0 / p.SPT, ks = u0 - tile * p.SPT;  // tracked incrementally (no division in the loop)
+  for (int it = 0; it < n_units; ++it) {
+    ptx::mbar_wait(&full[slot], phase);
+    const uint32_t wa = Wsm + slot * W_BYTES + (16 * warp + g) * KSTAGE;  // row g of this warp
+    const uint32_t wb = wa + 8 * KSTAGE;                                   // row g + 8
+    const uint32_t arow = Asm + slot * A_BYTES + g * A_STRIDE + (32 * tig) * 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int chunk = 2 * tig + h;  // 16-byte run: k = 16*chunk .. +15
+      const uint4 qa = ptx::lds128(wa + ((chunk ^ g) << 4));
+      const uint4 qb = ptx::lds128(wb + ((chunk ^ g) << 4));
+      uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+      if (has_tok) {
+        a0 = ptx::lds128(arow + 32 * h);
+        a1 = ptx::lds128(arow + 32 * h + 16);
+      }
+      const uint32_t wqa[4] = {qa.x, qa.y, qa.z, qa.w};
+      const uint32_t wqb[4] = {qb.x, qb.y, qb.z, qb.w};
+      const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t fr[4];
+        Cvt8<T>::run(wqa[e], fr[0], fr[2]);  // row g:   slots (2t,2t+1) and (2t+8,2t+9)
+        Cvt8<T>::run(wqb[e], fr[1], fr[3]);  // row g+8
+        if (e & 1)
+          ptx::mma_16816(acc2, fr, av[2 * e], av[2 * e + 1], acc2, T());
+        else
+          ptx::mma_16816(acc, fr, av[2 * e], av[2 * e + 1], acc, T());
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[slot]);
+    if (++slot == S) {
+      slot = 0;
+      phase ^= 1;
+    }
+
+    if (ks == p.SPT - 1 || it == n_units - 1) {
+      // D fragment: acc[0..1] = (column 16w+g, tokens 2t, 2t+1), acc[2..3] = column 16w+g+8
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = 2 * tig + (i & 1);
+        const int col = 16 * warp + g + 8 * (i >> 1);
+        if (tok < p.M) red[tok * BN8 + col] = acc[i] + acc2[i];
+        acc[i] = 0.f;
+        acc2[i] = 0.f;
+      }
+      ptx::named_bar_sync(1, CW * 32);
+      const int t = threadIdx.x;
+      const bool colthread = t < BN8;
+      const int n = tile * BN8 + t;
+      float v[MMAX];
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m) v[m] = (colthread && m < p.M) ? red[m * BN8 + t] : 0.f;
+
+      const int t_first = tile * p.SPT, t_last = t_first + p.SPT - 1;
+      const bool whole = (u0 <= t_first) && (u1 > t_last);
+      bool write_out = whole;
+      if (!whole) {
+        const int my_slot = c * 2 + ((tile == u0 / p.SPT) ? 0 : 1);
+        float* mine = p.partials + static_cast<size_t>(my_slot) * kSlotFloats;
+        if (colthread) {
+#pragma unroll
+          for (int m = 0; m < MMAX; ++m)
+            if (m < p.M) mine[m * BN8 + t] = v[m];
+        }
+        __threadfence();
+        ptx::named_bar_sync(1, CW * 32);
+        const int c_first = unit_owner(p.U, P, t_first), c_last = unit_owner(p.U, P, t_last);
+        if (t == 0) {
+          const int old = atomicAdd(&p.counters[tile], 1);
+          const int last = (old == c_last - c_first) ? 1 : 0;
+          if (last) p.counters[tile] = 0;
+          *flag = last;
+        }
+        ptx::named_bar_sync(1, CW * 32);
+        write_out = (*flag != 0);
+        if (write_out && colthread) {
+          __threadfence();
+#pragma unroll
+          for (int m = 0; m < MMAX; ++m) v[m] = 0.f;
+          for (int cc = c_first; cc <= c_last; ++cc) {
+            const int sl = cc * 2 + ((tile == unit_begin(p.U, P, cc) / p.SPT) ? 0 : 1);
+            const float* src = p.partials + static_cast<size_t>(sl) * kSlotFloats;
+#pragma unroll
+            for (int m = 0; m < MMAX; ++m)
+              if (m < p.M) v[m] += ptx::ldcg_f32(src + m * BN8 + t);
+          }
+        }
+      }
+      if (write_out && colthread && n < p.N) {
+        T* Cp = static_cast<T*>(p.C);
+        const T* bias = static_cast<const T*>(p.bias);
+        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+#pragma unroll
+        for (int m = 0; m < MMAX; ++m)
+          if (m < p.M) Cp[m * p.ldc + n] = epilogue<T>(v[m] * s, bias, n);
+      }
+      ptx::named_bar_sync(1, CW * 32);
+    }
+    if (++ks == p.SPT) {
+      ks = 0;
+      ++tile;
+    }
+  }
+}
+
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* s = getenv(name);
+  if (s == nullptr || *s == 0) return dflt;
+  int v = atoi(s);
+  if (v < lo) v = lo;
+  if (v > hi) v = hi;
+  return v;
+}
+
+template <typename T, bool kM1>
+int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, Params prm, int grid, size_t smem,
+                bool pdl) {
+  auto kern = w8_gemv_kernel<T, kM1>;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CGQ_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    configured[dev] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmW, prm));
+  return CGQ_OK;
+}
+
+template <typename T>
+int launch_t(const GemmArgs& a) {
+  const int SPT = (a.K + KSTAGE - 1) / KSTAGE;
+  const int tiles = (a.N + BN8 - 1) / BN8;
+  const int U = tiles * SPT;
+  static const int stages = env_int("CGQ_GEMV_STAGES", 8, 2, 16);
+  static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 2, 1, 4);
+  static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
+  int grid = sm_count() * cps;
+  if (grid > kMaxCtas) grid = kMaxCtas;
+  if (grid > U) grid = U;
+
+  CUtensorMap tmW;
+  TmapKey kw{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N),
+             static_cast<uint64_t>(a.K), KSTAGE, BN8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+             CU_TENSOR_MAP_SWIZZLE_128B};
+  int rc = get_tmap_2d(kw, &tmW);
+  if (rc != CGQ_OK) return rc;
+
+  Params prm;
+  prm.A = a.A;
+  prm.lda = a.lda;
+  prm.scale = a.scale;
+  prm.bias = a.bias;
+  prm.C = a.C;
+  prm.ldc = a.ldc;
+  prm.M = a.M;
+  prm.N = a.N;
+  prm.K = a.K;
+  prm.SPT = SPT;
+  prm.U = U;
+  prm.S = stages;
+  prm.counters = static_cast<int*>(a.workspace);
+  prm.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kCounterBytes);
+  const size_t smem =
+      1024 + static_cast<size_t>(stages) * (W_BYTES + A_BYTES) + RED_BYTES + 16 * stages + 16;
+  if (a.M == 1) return launch_inst<T, true>(a, tmW, prm, grid, smem, pdl);
+  return launch_inst<T, false>(a, tmW, prm, grid, smem, pdl);
+}
+
+}  // namespace
+
+bool w8_gemv_supported(const GemmArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int tiles = (a.N + BN8 - 1) / BN8;
+  return a.M >= 1 && a.M <= MMAX && a.K % 16 == 0 && al16(a.Wq) && al16(a.A) && a.lda % 8 == 0 &&
+         tiles <= kMaxTiles;
+}
+
+int launch_w8_gemv(const GemmArgs& a) {
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a) : launch_t<__nv_bfloat16>(a);
+}
+
+}  // namespace cgq

@@ -1,0 +1,38 @@
+"""Bind the sm_100a kernels behind an UNMODIFIED chatglm_q package (seam S1).
+
+`chatglm_q/int4/qlinear.py:7-17` and `chatglm_q/int8/qlinear.py:6-16` import their kernel entry
+points into module globals and look them up at call time (`int4/qlinear.py:47-48`), so rebinding
+those globals swaps the kernel for every existing module instance with zero reference edits.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import ops
+
+_saved: dict[str, dict[str, object]] = {}
+
+
+def install(package: str = "chatglm_q") -> None:
+    """Rebind `<package>.int4.qlinear` / `<package>.int8.qlinear` kernel globals to chatglm_q_b200."""
+    q4 = importlib.import_module(f"{package}.int4.qlinear")
+    q8 = importlib.import_module(f"{package}.int8.qlinear")
+    for mod, impl in ((q4, ops.dynamic_quant_matmul_s4), (q8, ops.dynamic_quant_matmul)):
+        if mod.__name__ not in _saved:
+            _saved[mod.__name__] = {
+                k: getattr(mod, k, None)
+                for k in ("_dynamic_quant_matmul_impl", "check_input", "KERNEL_IMPL")
+            }
+        mod._dynamic_quant_matmul_impl = impl
+        mod.check_input = ops.check_input
+        mod.KERNEL_IMPL = "cgq_b200"
+
+
+def uninstall(package: str = "chatglm_q") -> None:
+    for name in (f"{package}.int4.qlinear", f"{package}.int8.qlinear"):
+        saved = _saved.pop(name, None)
+        if saved is None:
+            continue
+        mod = importlib.import_module(name)
+        for k, v in saved.items():
+            setattr(mod, k, v)

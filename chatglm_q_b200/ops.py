@@ -1,0 +1,207 @@
+"""Host side of the dequant-matmul path: the same operator surface as the reference's
+`chatglm_q/int4/triton_ops.py` and `chatglm_q/int8/triton_ops.py` (names, argument meaning and
+error behaviour), bound to the sm_100a kernels through the C-ABI in include/cgq.h.
+
+torch is used for device memory, streams and nothing else: every function here ends in one
+`cgq_*` call with raw device pointers.  There is no CPU / eager fallback — a tensor the kernels
+cannot take raises.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_SIMPLE, IMPL_TC  # noqa: F401
+
+_DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
+_workspaces: dict[tuple[int, int], Tensor] = {}
+_ws_bytes = None
+
+
+def check_input(a: Tensor) -> bool:
+    """Reference: int4/triton_ops.py:10-11 — the fast path takes any CUDA tensor."""
+    return a.get_device() >= 0
+
+
+def _workspace(device: torch.device, stream: int) -> Tensor:
+    """Zero-initialised, self-cleaning stream-K workspace, one per (device, stream)."""
+    global _ws_bytes
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        if _ws_bytes is None:
+            _ws_bytes = int(_lib.load().cgq_workspace_bytes())
+        ws = torch.zeros(_ws_bytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _dtype_code(t: Tensor) -> int:
+    code = _DTYPE_CODE.get(t.dtype)
+    if code is None:
+        raise TypeError(
+            f"cgq kernels compute in float16/bfloat16 activations, got {t.dtype} "
+            "(no fp32 / CPU fallback exists on this path)")
+    return code
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def dynamic_quant_matmul_s4(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool = None,
+                            bias: Tensor = None, impl: int = IMPL_AUTO) -> Tensor:
+    """
+    a:        (..., K)   float16 / bfloat16, CUDA
+    b:        (K//2, N)  uint8, two K-adjacent int4 per byte (low nibble = even k), value = nibble - 8
+    b_scale:  (G, N)     same dtype as a, G = K // 32
+    returns:  (..., N)   new tensor, dtype of a
+
+    Drop-in for chatglm_q.int4.triton_ops.dynamic_quant_matmul_s4 (int4/triton_ops.py:90-139).
+    `allow_tf32` is accepted and ignored (16-bit inputs never used TF32).  `bias` (optional, [N])
+    fuses the module's `out += bias` into the epilogue with the same two roundings.
+    """
+    output_shape = (*a.shape[:-1], b.shape[1])
+    a = a.flatten(0, -2)
+    assert len(b.shape) == 2
+    assert len(b_scale.shape) == 2
+    assert a.shape[1] == b.shape[0] * 2
+    assert b.shape[1] == b_scale.shape[1]
+    assert b.dtype == torch.uint8
+    assert a.dtype == b_scale.dtype
+    assert b.shape[0] % b_scale.shape[0] == 0
+    assert a.get_device() >= 0
+    assert b.get_device() == a.get_device(), f"{b.device=}, {a.device=}"
+    assert b_scale.get_device() == a.get_device(), f"{b_scale.device=}, {a.device=}"
+    M, K = a.shape
+    G, N = b_scale.shape
+    group = K // G
+    assert group == 32, f"only the reference model's group size 32 is built, got {group}"
+    code = _dtype_code(a)
+    if a.stride(1) != 1 or (M > 1 and a.stride(0) < K):
+        a = a.contiguous()
+    if not b.is_contiguous():
+        b = b.contiguous()
+    if not b_scale.is_contiguous():
+        b_scale = b_scale.contiguous()
+    if bias is not None:
+        assert bias.shape == (N,) and bias.dtype == a.dtype and bias.get_device() == a.get_device()
+        bias = bias.contiguous()
+    c = torch.empty((M, N), device=a.device, dtype=a.dtype)
+    if M == 0:
+        return c.reshape(output_shape)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = _workspace(a.device, stream)
+        _lib.check(lib.cgq_w4a16_gemm_ex(
+            a.data_ptr(), a.stride(0) if M > 1 else K, b.data_ptr(), b_scale.data_ptr(), _ptr(bias),
+            c.data_ptr(), N, M, N, K, group, code, ws.data_ptr(), ws.numel(), stream, impl))
+    return c.reshape(output_shape)
+
+
+def dynamic_quant_matmul(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool = None,
+                         bias: Tensor = None, impl: int = IMPL_AUTO) -> Tensor:
+    """
+    a:        (..., K)  float16 / bfloat16, CUDA
+    b:        (K, N)    int8 — the `weight.t()` VIEW (strides (1, K)) of the module's [N, K] buffer
+    b_scale:  (N)       same dtype as a
+    returns:  (..., N)
+
+    Drop-in for chatglm_q.int8.triton_ops.dynamic_quant_matmul (int8/triton_ops.py:87-127).
+    The kernels read the weight K-contiguous, i.e. exactly the module buffer; a `b` that is not such
+    a transposed view is copied once into that layout.
+    """
+    output_shape = (*a.shape[:-1], b.shape[1])
+    a = a.flatten(0, -2)
+    assert len(b.shape) == 2
+    assert len(b_scale.shape) == 1
+    assert a.shape[1] == b.shape[0]
+    assert b.shape[1] == b_scale.shape[0]
+    assert b.dtype == torch.int8
+    assert a.dtype == b_scale.dtype
+    assert a.get_device() >= 0
+    assert b.get_device() == a.get_device(), f"{b.device=}, {a.device=}"
+    assert b_scale.get_device() == a.get_device(), f"{b_scale.device=}, {a.device=}"
+    M, K = a.shape
+    _, N = b.shape
+    code = _dtype_code(a)
+    if a.stride(1) != 1 or (M > 1 and a.stride(0) < K):
+        a = a.contiguous()
+    w_nk = b.t()  # [N, K]
+    if not w_nk.is_contiguous():
+        w_nk = w_nk.contiguous()
+    if not b_scale.is_contiguous():
+        b_scale = b_scale.contiguous()
+    if bias is not None:
+        assert bias.shape == (N,) and bias.dtype == a.dtype and bias.get_device() == a.get_device()
+        bias = bias.contiguous()
+    c = torch.empty((M, N), device=a.device, dtype=a.dtype)
+    if M == 0:
+        return c.reshape(output_shape)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = _workspace(a.device, stream)
+        _lib.check(lib.cgq_w8a16_gemm_ex(
+            a.data_ptr(), a.stride(0) if M > 1 else K, w_nk.data_ptr(), b_scale.data_ptr(),
+            _ptr(bias), c.data_ptr(), N, M, N, K, code, ws.data_ptr(), ws.numel(), stream, impl))
+    return c.reshape(output_shape)
+
+
+def unpack_int4_i8(x: Tensor) -> Tensor:
+    """[K/2, N] uint8 -> [K, N] int8 (nibble - 8); bit-exact twin of int4/qlinear.py:29-31."""
+    assert x.dtype == torch.uint8 and x.dim() == 2 and x.get_device() >= 0
+    x = x.contiguous()
+    K, N = x.shape[0] * 2, x.shape[1]
+    out = torch.empty((K, N), dtype=torch.int8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().cgq_w4_unpack_i8(x.data_ptr(), out.data_ptr(), K, N,
+                                               torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def unpack_int4(x: Tensor, x_scale: Tensor) -> Tensor:
+    """[K/2, N] uint8, [G, N] scale -> dequantised [K, N]; bit-exact twin of
+    chatglm_q.int4.qlinear.unpack_int4 (int4/qlinear.py:20-33)."""
+    assert x.dtype == torch.uint8 and x.dim() == 2 and x.get_device() >= 0
+    K = x.shape[0] * 2
+    G, N = x_scale.shape
+    assert x.shape[1] == N
+    assert K % G == 0, f"{K=}, {G=}"
+    code = _dtype_code(x_scale)
+    x, x_scale = x.contiguous(), x_scale.contiguous()
+    out = torch.empty((K, N), dtype=x_scale.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().cgq_w4_dequant(x.data_ptr(), x_scale.data_ptr(), out.data_ptr(), K, N,
+                                             K // G, code, torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def embedding_s4(ids: Tensor, weight: Tensor, weight_scale: Tensor, group_size: int = 32) -> Tensor:
+    """QEmbedding.forward of the int4 model (int4/qlinear.py:122-130)."""
+    assert ids.dtype == torch.int64 and ids.get_device() >= 0
+    code = _dtype_code(weight_scale)
+    V, D = weight.shape[0] * 2, weight.shape[1]
+    flat = ids.reshape(-1).contiguous()
+    out = torch.empty((flat.numel(), D), dtype=weight_scale.dtype, device=ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(_lib.load().cgq_w4_embedding(
+            flat.data_ptr(), flat.numel(), weight.data_ptr(), weight_scale.data_ptr(), out.data_ptr(),
+            V, D, group_size, code, torch.cuda.current_stream().cuda_stream))
+    return out.reshape(*ids.shape, D)
+
+
+def embedding_s8(ids: Tensor, weight: Tensor, weight_scale: Tensor) -> Tensor:
+    """QEmbedding.forward of the int8 model (int8/qlinear.py:118-120)."""
+    assert ids.dtype == torch.int64 and ids.get_device() >= 0
+    code = _dtype_code(weight_scale)
+    V, D = weight.shape
+    flat = ids.reshape(-1).contiguous()
+    out = torch.empty((flat.numel(), D), dtype=weight_scale.dtype, device=ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(_lib.load().cgq_w8_embedding(
+            flat.data_ptr(), flat.numel(), weight.data_ptr(), weight_scale.data_ptr(), out.data_ptr(),
+            V, D, code, torch.cuda.current_stream().cuda_stream))
+    return out.reshape(*ids.shape, D)

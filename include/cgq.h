@@ -1,0 +1,131 @@
+/*
+ * cgq.h — C-ABI of the B200-native (sm_100a) weight-only dequant-matmul path of chatglm-q.
+ *
+ * The reference (K024/chatglm-q) has no FFI: its GPU path is four Triton kernels bound to
+ * the module globals `_dynamic_quant_matmul_impl` / `check_input` of
+ *   chatglm_q/int4/qlinear.py:7-17   and   chatglm_q/int8/qlinear.py:6-16.
+ * This header DEFINES the boundary a maintainer would bind there (see INTEGRATION.md for the
+ * ctypes stub).  Every entry point states which reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all data pointers are DEVICE pointers on the current CUDA device;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - launches are asynchronous on `stream`; no host synchronisation inside any call;
+ *   - return value: CGQ_OK (0) or a negative CGQ_ERR_* code; `cgq_last_error()` has the text;
+ *   - no CPU fallback exists: an input the kernels cannot take is an error, never a slow path.
+ *
+ * dtype codes (activation / scale / output element type): 0 = IEEE fp16, 1 = bfloat16.
+ */
+#ifndef CGQ_H_
+#define CGQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGQ_OK 0
+#define CGQ_ERR_BAD_SHAPE (-1)      /* M,N,K / group inconsistent (reference: AssertionError, int4/triton_ops.py:102-123) */
+#define CGQ_ERR_BAD_DTYPE (-2)      /* dtype code not 0/1 (reference asserts a.dtype == b_scale.dtype, :108) */
+#define CGQ_ERR_MISALIGNED (-3)     /* pointer / leading dimension alignment not met */
+#define CGQ_ERR_CUDA (-4)           /* a CUDA runtime / driver call failed */
+#define CGQ_ERR_WORKSPACE (-5)      /* workspace NULL or smaller than cgq_workspace_bytes() */
+#define CGQ_ERR_UNSUPPORTED (-6)    /* device is not sm_100 */
+
+#define CGQ_DTYPE_F16 0
+#define CGQ_DTYPE_BF16 1
+
+/* Kernel selection for the *_ex entry points (tests / bench / profiling only). */
+#define CGQ_IMPL_AUTO 0             /* what cgq_w4a16_gemm / cgq_w8a16_gemm pick */
+#define CGQ_IMPL_SIMPLE 1           /* one-thread-per-column CUDA-core kernel, bit-faithful dequant */
+#define CGQ_IMPL_GEMV 2             /* TMA-fed stream-K mma kernel, M <= 8 (decode) */
+#define CGQ_IMPL_GEMV_EXACT 3       /* same, dequant via exact (q-8) fp16 subtraction instead of subnormal trick */
+#define CGQ_IMPL_TC 4               /* tcgen05 tensor-core GEMM (prefill) */
+
+/* Library / ABI version: (major << 16) | minor. */
+int cgq_version(void);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* cgq_last_error(void);
+
+/*
+ * Bytes of device workspace a GEMM call needs (stream-K partial tiles + self-cleaning tile
+ * counters).  The workspace must be zero-filled ONCE after allocation; every call leaves it
+ * zeroed again.  One workspace may not be shared by calls running concurrently on different
+ * streams.  The value is a constant upper bound, independent of the shape.
+ * Reference: none (the Triton kernels use no workspace, int4/triton_ops.py:124-138).
+ */
+size_t cgq_workspace_bytes(void);
+
+/*
+ * C[M,N] = A[M,K] · dequant(Wq, scale) (+ bias), int4 group-quantised weights.
+ * Replaces chatglm_q.int4.triton_ops.dynamic_quant_matmul_s4 (int4/triton_ops.py:90-139,
+ * kernel :18-87) and, with `bias`, the `out += self.bias` of
+ * DynamicQuantizeLinear.forward (int4/qlinear.py:90-94).
+ *
+ *   A      [M, K]    dtype, row stride `lda` elements, unit column stride
+ *   Wq     [K/2, N]  uint8, contiguous; byte (r, n) = nibble(k=2r) | nibble(k=2r+1) << 4,
+ *                    value = nibble - 8                        (int4/quantizer.py:25-28)
+ *   scale  [K/group, N] dtype, contiguous                      (int4/qlinear.py:84)
+ *   bias   [N] dtype or NULL; added AFTER the product is rounded to dtype (two roundings,
+ *                    as the reference's separate in-place add)
+ *   C      [M, N]    dtype, row stride `ldc` elements
+ *   group  must be 32 (the only group size the reference model builds, int4/qlinear.py:5,76)
+ */
+int cgq_w4a16_gemm(const void* A, int64_t lda, const uint8_t* Wq, const void* scale,
+                   const void* bias, void* C, int64_t ldc, int M, int N, int K, int group,
+                   int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with an explicit kernel choice (CGQ_IMPL_*). */
+int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, const void* scale,
+                      const void* bias, void* C, int64_t ldc, int M, int N, int K, int group,
+                      int dtype, void* workspace, size_t workspace_bytes, void* stream, int impl);
+
+/*
+ * C[M,N] = A[M,K] · (Wq^T * scale) (+ bias), int8 per-output-channel weights.
+ * Replaces chatglm_q.int8.triton_ops.dynamic_quant_matmul (int8/triton_ops.py:87-127,
+ * kernel :13-84) called with `weight.t()` by DynamicQuantizeLinear.forward
+ * (int8/qlinear.py:89-93).
+ *
+ *   Wq     [N, K] int8, contiguous (the module buffer itself, NOT the transposed view)
+ *   scale  [N] dtype (may be negative: tests/test_triton_ops.py:12)
+ */
+int cgq_w8a16_gemm(const void* A, int64_t lda, const int8_t* Wq, const void* scale,
+                   const void* bias, void* C, int64_t ldc, int M, int N, int K, int dtype,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, const void* scale,
+                      const void* bias, void* C, int64_t ldc, int M, int N, int K, int dtype,
+                      void* workspace, size_t workspace_bytes, void* stream, int impl);
+
+/*
+ * Unpack the int4 weight to signed integers: out_i8[K, N] = nibble - 8.  Bit-exact restatement
+ * of `((x >> shifts) & 0xF).to(int8) - 8` (int4/qlinear.py:29-31).  Test-only surface that
+ * carries the "int unpack bit-exact" claim.
+ */
+int cgq_w4_unpack_i8(const uint8_t* Wq, int8_t* out, int K, int N, void* stream);
+
+/*
+ * Dequantise the int4 weight: out[K, N] (dtype) = round_dtype((nibble - 8) * scale[k/group, n]).
+ * Bit-exact restatement of chatglm_q.int4.qlinear.unpack_int4 (int4/qlinear.py:20-33).
+ */
+int cgq_w4_dequant(const uint8_t* Wq, const void* scale, void* out, int K, int N, int group,
+                   int dtype, void* stream);
+
+/*
+ * Embedding row gather + dequant for the int4 / int8 QEmbedding modules
+ * (int4/qlinear.py:122-130: packed along the VOCAB axis, 2 tokens per byte, groups of 32 tokens;
+ *  int8/qlinear.py:118-120).  ids are int64 token ids, out is [n_ids, dim] dtype.
+ */
+int cgq_w4_embedding(const int64_t* ids, int n_ids, const uint8_t* Wq /*[V/2, D]*/,
+                     const void* scale /*[V/group, D]*/, void* out, int V, int D, int group,
+                     int dtype, void* stream);
+int cgq_w8_embedding(const int64_t* ids, int n_ids, const int8_t* Wq /*[V, D]*/,
+                     const void* scale /*[D]*/, void* out, int V, int D, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGQ_H_ */

@@ -1,0 +1,275 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI (chatglm_q_b200.ops -> libcgq.so),
+against the oracle on identical seeded inputs, the committed golden fixtures from the real
+reference, and size-independent properties at BASELINE.json's full sizes.
+
+Parity bar: integer unpack and the dequantised weight are BIT-EXACT; the matmul is within
+1e-2 (util.assert_parity: |got-ref| <= 1e-2*|ref| + 1e-2*rms(ref)), BASELINE.json north_star.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import qmatmul_oracle as orc
+from util import (assert_parity, from_torch, load16, make_int4_case, make_int8_case, to_torch)
+
+pytestmark = pytest.mark.gpu
+
+from chatglm_q_b200 import int4 as m4  # noqa: E402
+from chatglm_q_b200 import int8 as m8  # noqa: E402
+from chatglm_q_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+IMPLS4 = {"auto": ops.IMPL_AUTO, "simple": ops.IMPL_SIMPLE, "gemv": ops.IMPL_GEMV,
+          "gemv_exact": ops.IMPL_GEMV_EXACT}
+
+
+def u8(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def run4(a, bq, s, dtype, bias=None, impl=ops.IMPL_AUTO):
+    out = ops.dynamic_quant_matmul_s4(to_torch(a, dtype), u8(bq), to_torch(s, dtype),
+                                      bias=None if bias is None else to_torch(bias, dtype), impl=impl)
+    torch.cuda.synchronize()
+    return from_torch(out)
+
+
+def run8(a, q_nk, s, dtype, bias=None, impl=ops.IMPL_AUTO):
+    w = u8(q_nk)  # [N, K] module buffer; the op takes the transposed view like the reference forward
+    out = ops.dynamic_quant_matmul(to_torch(a, dtype), w.t(), to_torch(s, dtype),
+                                   bias=None if bias is None else to_torch(bias, dtype), impl=impl)
+    torch.cuda.synchronize()
+    return from_torch(out)
+
+
+# ------------------------------------------------------------------ bit-exact pieces
+def test_unpack_i8_bit_exact(golden):
+    got = ops.unpack_int4_i8(u8(golden["unpack_bytes"])).cpu().numpy()
+    assert np.array_equal(got, golden["unpack_i8"])
+    rng = np.random.default_rng(7)
+    b = rng.integers(0, 256, size=(2048, 272), dtype=np.uint8)
+    assert np.array_equal(ops.unpack_int4_i8(u8(b)).cpu().numpy(), orc.unpack_int4_i8(b))
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_dequant_bit_exact(golden, dtype):
+    scale = load16(golden[f"unpack_scale_{dtype}"], dtype)
+    want = load16(golden[f"unpack_out_{dtype}"], dtype)
+    got = from_torch(ops.unpack_int4(u8(golden["unpack_bytes"]), to_torch(scale, dtype)))
+    assert np.array_equal(got, want)
+    # random bytes (2048, 64), includes nibble 0 and tiny / negative scales
+    rng = np.random.default_rng(11)
+    b = rng.integers(0, 256, size=(2048, 64), dtype=np.uint8)
+    s = orc.round_to(rng.standard_normal((128, 64)) * 0.01, dtype)
+    got = from_torch(ops.unpack_int4(u8(b), to_torch(s, dtype)))
+    assert np.array_equal(got, orc.unpack_int4(b, s, dtype))
+
+
+def test_embeddings_bit_exact(golden):
+    ids = torch.from_numpy(golden["e4_ids"]).to(DEV)
+    got = from_torch(ops.embedding_s4(ids, u8(golden["e4_bytes"]),
+                                      torch.from_numpy(golden["e4_scale"]).to(DEV)))
+    assert np.array_equal(got, golden["e4_y"].astype(np.float32))
+    got8 = from_torch(ops.embedding_s8(ids, u8(golden["e8_q"]), torch.from_numpy(golden["e8_scale"]).to(DEV)))
+    assert np.array_equal(got8, golden["e8_y"].astype(np.float32))
+
+
+# ------------------------------------------------------------------ golden fixtures from the reference
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("impl", ["auto", "simple", "gemv_exact"])
+def test_int4_linear_golden(golden, dtype, impl):
+    x = load16(golden[f"l4_x_{dtype}"], dtype)
+    s = load16(golden[f"l4_scale_{dtype}"], dtype)
+    b = load16(golden[f"l4_bias_{dtype}"], dtype)
+    want = load16(golden[f"l4_y_{dtype}"], dtype)
+    got = run4(x, golden["l4_bytes"], s, dtype, bias=b, impl=IMPLS4[impl])
+    assert_parity(got, want, f"int4 golden {dtype} {impl}")
+
+
+def test_int4_reference_test_shape(golden):
+    """tests/test_triton_ops_int4.py:11-22 inputs, run in fp16 (the kernels take 16-bit activations)."""
+    a = orc.round_to(golden["t4_a"], "float16")
+    s = orc.round_to(golden["t4_scale"], "float16")
+    got = run4(a, golden["t4_bytes"], s, "float16")
+    assert_parity(got, orc.qmatmul_int4(a, golden["t4_bytes"], s, None, "float16"), "int4 ref-test shape")
+    # and against the fp32 result the reference test itself expects, at the 16-bit parity bar
+    assert_parity(got, golden["t4_y"], "int4 ref-test shape vs fp32 golden", rtol=2e-2)
+
+
+def test_int8_reference_test_shape(golden):
+    """tests/test_triton_ops.py:9-17: M=10 (ragged row block), signed scales."""
+    a = orc.round_to(golden["t8_a"], "float16")
+    s = orc.round_to(golden["t8_scale"], "float16")
+    w_nk = np.ascontiguousarray(golden["t8_b_kn"].T)
+    got = run8(a, w_nk, s, "float16")
+    assert_parity(got, orc.qmatmul_int8(a, w_nk, s, None, "float16"), "int8 ref-test shape")
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_int8_linear_golden(golden, dtype):
+    x = load16(golden[f"l8_x_{dtype}"], dtype)
+    s = load16(golden[f"l8_scale_{dtype}"], dtype)
+    b = load16(golden[f"l8_bias_{dtype}"], dtype)
+    want = load16(golden[f"l8_y_{dtype}"], dtype)
+    for impl in (ops.IMPL_AUTO, ops.IMPL_SIMPLE):
+        assert_parity(run8(x, golden["l8_q"], s, dtype, bias=b, impl=impl), want, f"int8 golden {dtype}")
+
+
+# ------------------------------------------------------------------ decode kernels vs oracle, real shapes
+SHAPES4 = [(4096, 4608), (4096, 4096), (13696, 4096), (4096, 1280), (512, 256), (4096, 6848)]
+
+
+@pytest.mark.parametrize("impl", ["gemv", "gemv_exact", "simple"])
+@pytest.mark.parametrize("kind", ["Q", "R"])
+@pytest.mark.parametrize("m", [1, 2, 5, 8])
+def test_int4_decode_shapes(impl, kind, m):
+    for (k, n) in SHAPES4:
+        a, bq, s = make_int4_case(1234 + 1000 * m + n, m, k, n, kind)
+        want = c_oracle.w4a16_gemm(a, bq, s, None, "float16")
+        got = run4(a, bq, s, "float16", impl=IMPLS4[impl])
+        assert_parity(got, want, f"int4 {impl} {kind} M={m} K={k} N={n}")
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_int4_decode_big_shapes(dtype):
+    """w_in (N=27392) and a 1/8 slice of lm_head width, bias on the qkv shape, bf16 too."""
+    for (m, k, n, with_bias) in [(1, 4096, 27392, False), (1, 4096, 4608, True), (8, 4096, 8128, True)]:
+        a, bq, s = make_int4_case(99 + n + m, m, k, n, "Q", dtype)
+        bias = orc.round_to(np.random.default_rng(n).standard_normal(n) * 0.1, dtype) if with_bias else None
+        want = c_oracle.w4a16_gemm(a, bq, s, bias, dtype)
+        assert_parity(run4(a, bq, s, dtype, bias=bias), want, f"int4 big {dtype} M={m} N={n}")
+
+
+@pytest.mark.parametrize("kind", ["Q", "R"])
+@pytest.mark.parametrize("m", [1, 3, 8])
+def test_int8_decode_shapes(kind, m):
+    for (k, n) in [(4096, 4608), (4096, 4096), (13696, 4096), (128, 256), (4096, 1000)]:
+        a, q, s = make_int8_case(4321 + 1000 * m + n, m, k, n, kind)
+        want = c_oracle.w8a16_gemm(a, q, s, None, "float16")
+        for impl in (ops.IMPL_AUTO, ops.IMPL_SIMPLE):
+            assert_parity(run8(a, q, s, "float16", impl=impl), want, f"int8 {kind} M={m} K={k} N={n} impl={impl}")
+
+
+def test_int8_bf16_and_bias():
+    a, q, s = make_int8_case(5, 4, 4096, 4608, "Q", "bfloat16")
+    bias = orc.round_to(np.random.default_rng(3).standard_normal(4608) * 0.1, "bfloat16")
+    assert_parity(run8(a, q, s, "bfloat16", bias=bias), c_oracle.w8a16_gemm(a, q, s, bias, "bfloat16"), "int8 bf16")
+
+
+# ------------------------------------------------------------------ prefill-sized M (M > 8)
+@pytest.mark.parametrize("m", [9, 32, 128, 300])
+def test_int4_prefill_m(m):
+    k, n = 4096, 1280
+    a, bq, s = make_int4_case(77 + m, m, k, n, "Q")
+    assert_parity(run4(a, bq, s, "float16"), c_oracle.w4a16_gemm(a, bq, s, None, "float16"), f"int4 M={m}")
+
+
+@pytest.mark.parametrize("m", [10, 128])
+def test_int8_prefill_m(m):
+    k, n = 4096, 768
+    a, q, s = make_int8_case(78 + m, m, k, n, "Q")
+    assert_parity(run8(a, q, s, "float16"), c_oracle.w8a16_gemm(a, q, s, None, "float16"), f"int8 M={m}")
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_shapes_and_strides():
+    # N not a multiple of 16 -> shape-general kernel; leading dims are flattened; empty batch
+    a, bq, s = make_int4_case(3, 6, 64, 40, "R")
+    want = orc.qmatmul_int4(a, bq, s, None, "float16")
+    assert_parity(run4(a, bq, s, "float16"), want, "N=40")
+    x = to_torch(a, "float16").reshape(2, 3, 64)
+    out = ops.dynamic_quant_matmul_s4(x, u8(bq), to_torch(s, "float16"))
+    assert out.shape == (2, 3, 40)
+    assert_parity(from_torch(out).reshape(6, 40), want, "leading dims")
+    empty = ops.dynamic_quant_matmul_s4(x[:0], u8(bq), to_torch(s, "float16"))
+    assert empty.shape == (0, 3, 40)
+    # row-strided activations (a slice of a wider tensor), decode kernel
+    a2, bq2, s2 = make_int4_case(4, 4, 4096, 512, "Q")
+    wide = torch.zeros(4, 8192, dtype=torch.float16, device=DEV)
+    wide[:, :4096] = to_torch(a2, "float16")
+    got = from_torch(ops.dynamic_quant_matmul_s4(wide[:, :4096], u8(bq2), to_torch(s2, "float16")))
+    assert_parity(got, c_oracle.w4a16_gemm(a2, bq2, s2, None, "float16"), "row-strided A")
+    # the output is a fresh tensor the caller may modify in place (reference: `out += self.bias`)
+    o1 = ops.dynamic_quant_matmul_s4(to_torch(a2, "float16"), u8(bq2), to_torch(s2, "float16"))
+    o1 += 1.0
+
+
+def test_unsupported_inputs_raise():
+    a, bq, s = make_int4_case(3, 2, 64, 32, "Q")
+    with pytest.raises(TypeError):  # fp32 activations: no fallback exists
+        ops.dynamic_quant_matmul_s4(to_torch(a, "float32"), u8(bq), to_torch(s, "float32"))
+    with pytest.raises(AssertionError):  # group size 64
+        ops.dynamic_quant_matmul_s4(to_torch(a, "float16"), u8(bq), to_torch(s[:1], "float16"))
+    with pytest.raises(AssertionError):  # weight on another device (CPU)
+        ops.dynamic_quant_matmul_s4(to_torch(a, "float16"), torch.from_numpy(bq), to_torch(s, "float16"))
+
+
+# ------------------------------------------------------------------ size-independent properties, full sizes
+@pytest.mark.parametrize("n", [4608, 13696, 27392, 65024])
+def test_properties_full_size_int4(n):
+    k = 4096
+    g = torch.Generator(device=DEV).manual_seed(n)
+    bq = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+    s = (torch.rand((k // 32, n), device=DEV, generator=g) * 0.02 - 0.01).half()
+    a = torch.randn((1, k), device=DEV, generator=g).half()
+    y1 = ops.dynamic_quant_matmul_s4(a, bq, s)
+    y2 = ops.dynamic_quant_matmul_s4(a, bq, s)
+    assert torch.equal(y1, y2), "deterministic reduction: two launches must agree bit-for-bit"
+    assert torch.isfinite(y1).all()
+    # scaling every scale by 2 doubles the result exactly (power of two)
+    assert torch.equal(ops.dynamic_quant_matmul_s4(a, bq, s * 2), y1 * 2)
+    # one-hot activation selects a dequantised weight row bit-exactly
+    w = ops.unpack_int4(bq, s)
+    for kk in (0, 1, 2047, 4095):
+        e = torch.zeros((1, k), dtype=torch.float16, device=DEV)
+        e[0, kk] = 1.0
+        assert torch.equal(ops.dynamic_quant_matmul_s4(e, bq, s)[0], w[kk]), f"one-hot k={kk}"
+    # all nibbles == 8 is the zero weight
+    z = ops.dynamic_quant_matmul_s4(a, torch.full_like(bq, 0x88), s)
+    assert (z == 0).all()
+    # fast kernel vs the bit-faithful CUDA-core kernel on the same inputs
+    ys = ops.dynamic_quant_matmul_s4(a, bq, s, impl=ops.IMPL_SIMPLE)
+    assert_parity(from_torch(y1), from_torch(ys), f"gemv vs simple N={n}")
+    # the repeated-run workspace stays clean: a different shape right after still agrees
+    a8 = torch.randn((8, k), device=DEV, generator=g).half()
+    y8 = ops.dynamic_quant_matmul_s4(a8, bq, s)
+    assert_parity(from_torch(y8), from_torch(ops.dynamic_quant_matmul_s4(a8, bq, s, impl=ops.IMPL_SIMPLE)),
+                  f"M=8 N={n}")
+
+
+def test_properties_full_size_int8():
+    k, n = 4096, 27392
+    g = torch.Generator(device=DEV).manual_seed(8)
+    w = torch.randint(-128, 128, (n, k), dtype=torch.int8, device=DEV, generator=g)
+    s = (torch.randn(n, device=DEV, generator=g) / 2048).half()
+    a = torch.randn((1, k), device=DEV, generator=g).half()
+    y1 = ops.dynamic_quant_matmul(a, w.t(), s)
+    assert torch.equal(y1, ops.dynamic_quant_matmul(a, w.t(), s))
+    assert torch.equal(ops.dynamic_quant_matmul(a, w.t(), s * 2), y1 * 2)
+    e = torch.zeros((1, k), dtype=torch.float16, device=DEV)
+    e[0, 77] = 1.0
+    want = (w[:, 77].float() * s.float()).half()
+    assert torch.equal(ops.dynamic_quant_matmul(e, w.t(), s)[0], want)
+    assert_parity(from_torch(y1), from_torch(ops.dynamic_quant_matmul(a, w.t(), s, impl=ops.IMPL_SIMPLE)), "int8 full")
+
+
+# ------------------------------------------------------------------ module-level seam (S2)
+def test_module_forward_matches_oracle():
+    k, n, m = 4096, 4608, 3
+    a, bq, s = make_int4_case(21, m, k, n, "Q")
+    bias = orc.round_to(np.random.default_rng(2).standard_normal(n) * 0.02, "float16")
+    lin = m4.DynamicQuantizeLinear(k, n, bias=True, device=DEV, dtype=torch.float16)
+    lin.apply_weights_(u8(bq), to_torch(s, "float16"), to_torch(bias, "float16"))
+    with torch.no_grad():
+        y = lin(to_torch(a, "float16").reshape(1, m, k))
+    assert y.shape == (1, m, n)
+    assert_parity(from_torch(y)[0], c_oracle.w4a16_gemm(a, bq, s, bias, "float16"), "W4Linear")
+    a8, q8, s8 = make_int8_case(22, m, k, n, "Q")
+    lin8 = m8.DynamicQuantizeLinear(k, n, bias=False, device=DEV, dtype=torch.float16)
+    lin8.apply_weights_(u8(q8), to_torch(s8, "float16"))
+    with torch.no_grad():
+        y8 = lin8(to_torch(a8, "float16"))
+    assert_parity(from_torch(y8), c_oracle.w8a16_gemm(a8, q8, s8, None, "float16"), "W8Linear")
+    with pytest.raises(RuntimeError):  # inference only
+        m4.dynamic_quant_matmul(to_torch(a, "float16").requires_grad_(), u8(bq), to_torch(s, "float16"))

@@ -1,0 +1,144 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/cgq.h declares, host-side
+validation mirrors the reference's AssertionErrors, the module mirrors keep the reference's
+state-dict contract, and the product never routes through the oracle."""
+import re
+import types
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    text = (ROOT / "include" / "cgq.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from chatglm_q_b200 import _lib
+
+    lib = _lib.load()  # no compute call: needs no GPU
+    names = header_symbols()
+    assert len(names) >= 11
+    for name in names:
+        assert hasattr(lib, name), f"libcgq.so does not export {name}"
+        assert name in _lib.SYMBOLS, f"ctypes binding lacks {name}"
+    assert lib.cgq_version() >= 1
+    assert lib.cgq_workspace_bytes() > 0
+
+
+def test_abi_argument_errors_without_gpu():
+    """Bad arguments are rejected before any CUDA work (status codes of include/cgq.h)."""
+    from chatglm_q_b200 import _lib
+
+    lib = _lib.load()
+    P = 0x10000  # never dereferenced: validation fails first
+    # group != 32
+    rc = lib.cgq_w4a16_gemm(P, 64, P, P, None, P, 8, 1, 8, 64, 16, 0, None, 0, None)
+    assert rc == -1 and b"group" in lib.cgq_last_error()
+    # dtype code
+    rc = lib.cgq_w4a16_gemm(P, 64, P, P, None, P, 8, 1, 8, 64, 32, 7, None, 0, None)
+    assert rc == -2
+    rc = lib.cgq_w8a16_gemm(P, 64, P, P, None, P, 8, 1, 8, -5, 0, None, 0, None)
+    assert rc == -1
+    rc = lib.cgq_w4_unpack_i8(P, P, 7, 8, None)  # odd K
+    assert rc == -1
+    with pytest.raises(_lib.CgqError):
+        _lib.check(rc)
+
+
+def test_product_never_imports_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[./]|qmatmul_oracle|liboracle", re.M)
+    for f in (ROOT / "chatglm_q_b200").rglob("*"):
+        if f.suffix in {".py", ".cu", ".cuh", ".h"}:
+            assert not pat.search(f.read_text()), f"{f} references the oracle"
+
+
+def test_host_checks_mirror_reference_asserts():
+    from chatglm_q_b200 import ops
+
+    a = torch.zeros(2, 64, dtype=torch.float16)
+    b = torch.zeros(32, 16, dtype=torch.uint8)
+    s = torch.zeros(2, 16, dtype=torch.float16)
+    assert ops.check_input(a) is False  # CPU tensor: the reference would take its torch fallback
+    with pytest.raises(AssertionError):  # int4/triton_ops.py:109 `assert a.get_device() >= 0`
+        ops.dynamic_quant_matmul_s4(a, b, s)
+    with pytest.raises(AssertionError):  # :104 shape mismatch
+        ops.dynamic_quant_matmul_s4(torch.zeros(2, 60, dtype=torch.float16), b, s)
+    with pytest.raises(AssertionError):  # :106 dtype of B
+        ops.dynamic_quant_matmul_s4(a, b.to(torch.int8), s)
+    with pytest.raises(AssertionError):  # :107 a.dtype == b_scale.dtype
+        ops.dynamic_quant_matmul_s4(a, b, s.float())
+    with pytest.raises(AssertionError):  # int8/triton_ops.py:98 scale must be 1-D
+        ops.dynamic_quant_matmul(a, torch.zeros(64, 16, dtype=torch.int8), s)
+
+
+def test_module_mirrors_keep_state_dict_contract():
+    from chatglm_q_b200 import int4, int8
+
+    m4 = int4.DynamicQuantizeLinear(4096, 4608, bias=True, dtype=torch.float16, device="meta")
+    sd = m4.state_dict()
+    assert list(sd) == ["weight", "weight_scale", "bias"]
+    assert sd["weight"].shape == (2048, 4608) and sd["weight"].dtype == torch.uint8
+    assert sd["weight_scale"].shape == (128, 4608) and sd["weight_scale"].dtype == torch.float16
+    assert sd["bias"].shape == (4608,)
+    assert not list(m4.parameters())  # buffers, not parameters (int4/qlinear.py:83-88)
+    m4n = int4.DynamicQuantizeLinear(13696, 4096, bias=False, dtype=torch.float16, device="meta")
+    assert list(m4n.state_dict()) == ["weight", "weight_scale"] and m4n.bias is None
+    assert m4n.weight_scale.shape == (428, 4096)
+    with pytest.raises(AssertionError):
+        int4.DynamicQuantizeLinear(100, 8)  # in_features % group_size
+    m8 = int8.DynamicQuantizeLinear(4096, 27392, bias=False, dtype=torch.float16, device="meta")
+    assert m8.weight.shape == (27392, 4096) and m8.weight.dtype == torch.int8
+    assert m8.weight_scale.shape == (27392,)
+    e4 = int4.QEmbedding(65024, 4096, dtype=torch.float16, device="meta")
+    assert e4.weight.shape == (32512, 4096) and e4.weight_scale.shape == (2032, 4096)
+    e8 = int8.QEmbedding(65024, 4096, dtype=torch.float16, device="meta")
+    assert e8.weight.shape == (65024, 4096) and e8.weight_scale.shape == (4096,)
+    # apply_weights_ fills in place (quantiser scripts rely on it)
+    m = int4.DynamicQuantizeLinear(64, 16, bias=True, dtype=torch.float16)
+    m.apply_weights_(torch.full((32, 16), 0x88, dtype=torch.uint8), torch.ones(2, 16), torch.zeros(16))
+    assert int(m.weight[0, 0]) == 0x88 and float(m.weight_scale[1, 3]) == 1.0
+
+
+def test_install_rebinds_reference_globals():
+    """Seam S1: chatglm_q.int4.qlinear._dynamic_quant_matmul_impl / check_input are module globals."""
+    import sys
+
+    from chatglm_q_b200 import install, ops
+
+    pkg = "fake_chatglm_q"
+    mods = {}
+    for name in (pkg, f"{pkg}.int4", f"{pkg}.int4.qlinear", f"{pkg}.int8", f"{pkg}.int8.qlinear"):
+        mods[name] = types.ModuleType(name)
+        mods[name].__path__ = []
+    sentinel = object()
+    for leaf in (f"{pkg}.int4.qlinear", f"{pkg}.int8.qlinear"):
+        mods[leaf]._dynamic_quant_matmul_impl = sentinel
+        mods[leaf].check_input = None
+        mods[leaf].KERNEL_IMPL = "none"
+    sys.modules.update(mods)
+    try:
+        install.install(pkg)
+        assert mods[f"{pkg}.int4.qlinear"]._dynamic_quant_matmul_impl is ops.dynamic_quant_matmul_s4
+        assert mods[f"{pkg}.int8.qlinear"]._dynamic_quant_matmul_impl is ops.dynamic_quant_matmul
+        assert mods[f"{pkg}.int4.qlinear"].check_input is ops.check_input
+        assert mods[f"{pkg}.int4.qlinear"].KERNEL_IMPL == "cgq_b200"
+        install.uninstall(pkg)
+        assert mods[f"{pkg}.int4.qlinear"]._dynamic_quant_matmul_impl is sentinel
+        assert mods[f"{pkg}.int8.qlinear"].KERNEL_IMPL == "none"
+    finally:
+        for name in mods:
+            sys.modules.pop(name, None)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from chatglm_q_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libcgq.so")
+    with pytest.raises(ImportError, match="no CPU / PyTorch fallback"):
+        _lib.load()
