@@ -21,6 +21,7 @@ SYMBOLS = {
                                c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "cgq_w8a16_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int]),
+    "cgq_debug_trace": (None, [c_void_p]),
     "cgq_w4_unpack_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cgq_w4_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cgq_w4_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -39,6 +39,13 @@ int sm_count() {
   return cached[dev];
 }
 
+static thread_local void* g_trace = nullptr;
+void* take_trace_buffer() {
+  void* t = g_trace;
+  g_trace = nullptr;
+  return t;
+}
+
 static int check_device() {
   static int ok[64] = {0};  // 0 unknown, 1 ok, -1 bad
   int dev = 0;
@@ -175,6 +182,7 @@ using namespace cgq;
 extern "C" int cgq_version(void) { return (0 << 16) | 1; }
 extern "C" const char* cgq_last_error(void) { return g_err; }
 extern "C" size_t cgq_workspace_bytes(void) { return kWorkspaceBytes; }
+extern "C" void cgq_debug_trace(void* device_buffer) { g_trace = device_buffer; }
 
 extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, const void* scale,
                                  const void* bias, void* C, int64_t ldc, int M, int N, int K,

@@ -63,11 +63,12 @@ __device__ __forceinline__ T epilogue(float acc, const T* bias, int n) {
 }
 
 // ------------------------------------------------------------------ workspace layout
-// [0, kCounterBytes)            : int32 tile counters (self-cleaning)
+// [0, kCounterBytes)            : int32 tile counters (self-cleaning), one per 128-byte line
 // [kCounterBytes, total)        : fp32 stream-K partial tiles, 2 slots per CTA
 constexpr int kMaxCtas = 148 * 4;
 constexpr int kMaxTiles = 8192;
-constexpr size_t kCounterBytes = sizeof(int) * kMaxTiles;
+constexpr int kCounterStride = 32;  // ints: one 128-byte line per tile counter (atomics on one line serialise)
+constexpr size_t kCounterBytes = sizeof(int) * kCounterStride * kMaxTiles;
 constexpr size_t kSlotFloats = 8 * 128;  // M_MAX x BN
 constexpr size_t kWorkspaceBytes = kCounterBytes + sizeof(float) * kSlotFloats * 2 * kMaxCtas;
 
@@ -94,5 +95,7 @@ bool w4_gemv_supported(const GemmArgs& a);
 bool w8_gemv_supported(const GemmArgs& a);
 
 int sm_count();
+// One-shot timeline buffer for the next decode-kernel launch (cgq_debug_trace); nullptr if none.
+void* take_trace_buffer();
 
 }  // namespace cgq

@@ -4,6 +4,11 @@
 // HBM-bound design (B200: 148 SMs, ~6.5 TB/s measured):
 //   * persistent stream-K grid: the (column-tile, k-stage) units are cut into gridDim.x equal
 //     contiguous ranges, so every SM streams the same number of bytes whatever N is;
+//   * small CTAs (4 consumer warps + 1 producer warp, ~50 KB of shared memory at M=1), two per SM
+//     per launch, so that the CTAs of the NEXT launch fit beside them: with programmatic dependent
+//     launch the next kernel's producers fill their rings with weights (which do not depend on the
+//     previous kernel) while this kernel is still computing — the HBM stream does not stop at
+//     kernel boundaries, which is what a chain of 1.5 µs GEMVs needs;
 //   * one producer lane per CTA feeds an S-deep shared-memory ring with TMA: a [64 x 128] byte
 //     tile of packed weights (128-byte swizzle), the [4 x 128] scale tile, and the matching
 //     128-k slice of each activation row (cp.async.bulk), all landing on one mbarrier;
@@ -37,9 +42,15 @@ constexpr int MMAX = 8;            // token rows (MMA n)
 constexpr int A_STRIDE = KSTAGE * 2 + 32;  // bytes per token row of the activation slice (+32: banks)
 constexpr int W_BYTES = ROWS * BN;
 constexpr int S_BYTES = CW * BN * 2;
-constexpr int A_BYTES = MMAX * A_STRIDE;
-constexpr int RED_BYTES = CW * MMAX * BN * 4;
 constexpr int kThreads = (CW + 1) * 32;
+
+template <bool kM1>
+struct Cfg {
+  static constexpr int MR = kM1 ? 1 : MMAX;           // token rows staged / reduced
+  static constexpr int A_BYTES = MR * A_STRIDE;
+  static constexpr int RED_BYTES = CW * MR * BN * 4;
+  static constexpr int STAGE_BYTES = W_BYTES + S_BYTES + A_BYTES;
+};
 
 static_assert(kSlotFloats == MMAX * BN, "workspace slot size");
 
@@ -104,6 +115,7 @@ struct Params {
   int S;       // ring depth
   int* counters;
   float* partials;
+  unsigned long long* trace;  // optional timeline (cgq_debug_trace), 8 words per CTA
 };
 
 __device__ __forceinline__ int unit_begin(int U, int P, int c) {
@@ -112,11 +124,20 @@ __device__ __forceinline__ int unit_begin(int U, int P, int c) {
 __device__ __forceinline__ int unit_owner(int U, int P, int u) {
   return static_cast<int>((static_cast<int64_t>(u + 1) * P - 1) / U);
 }
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 
 template <typename T, bool kTrick, bool kM1>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     w4_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmS,
                    const Params p) {
+  using C = Cfg<kM1>;
+  constexpr int MR = C::MR;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));  // generic pointer to aligned base
@@ -124,9 +145,9 @@ __global__ void __launch_bounds__(kThreads)
   const uint32_t Wsm = base;
   const uint32_t Ssm = Wsm + S * W_BYTES;
   const uint32_t Asm = Ssm + S * S_BYTES;
-  const uint32_t off_red = S * (W_BYTES + S_BYTES + A_BYTES);
+  const uint32_t off_red = S * C::STAGE_BYTES;
   float* red = reinterpret_cast<float*>(gen + off_red);
-  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + RED_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES);
   uint64_t* empty = full + S;
   int* flag = reinterpret_cast<int*>(empty + S);
 
@@ -136,8 +157,9 @@ __global__ void __launch_bounds__(kThreads)
   const int n_units = u1 - u0;
   const T* A = static_cast<const T*>(p.A);
 
+  if (threadIdx.x == 0) stamp(p, 0);
   // ---- prologue: barriers, zeroed activation ring (k >= K of a ragged last stage must read 0)
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == CW * 32) {
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmS);
     for (int s = 0; s < S; ++s) {
@@ -146,7 +168,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     ptx::fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < S * A_BYTES / 16; i += kThreads)
+  for (int i = threadIdx.x; i < S * C::A_BYTES / 16; i += kThreads)
     ptx::sts128(Asm + i * 16, make_uint4(0, 0, 0, 0));
   ptx::fence_proxy_async_smem();
   __syncthreads();
@@ -156,6 +178,7 @@ __global__ void __launch_bounds__(kThreads)
   if (warp == CW) {
     // =========================== producer: one lane drives TMA ===========================
     if (lane == 0) {
+      stamp(p, 1);
       const uint64_t pol = ptx::policy_evict_first();
       auto issue_w = [&](int i, int slot) {
         const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
@@ -168,10 +191,14 @@ __global__ void __launch_bounds__(kThreads)
       auto issue_a = [&](int i, int slot) {
         const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
         const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
-        uint8_t* dst = gen + S * (W_BYTES + S_BYTES) + slot * A_BYTES;
-        for (int m = 0; m < p.M; ++m)
-          ptx::bulk_load_1d(dst + m * A_STRIDE, A + m * p.lda + ks * KSTAGE, kvalid * 2,
-                            &full[slot]);
+        uint8_t* dst = gen + S * (W_BYTES + S_BYTES) + slot * C::A_BYTES;
+        if (kM1) {
+          ptx::bulk_load_1d(dst, A + ks * KSTAGE, kvalid * 2, &full[slot]);
+        } else {
+          for (int m = 0; m < p.M; ++m)
+            ptx::bulk_load_1d(dst + m * A_STRIDE, A + m * p.lda + ks * KSTAGE, kvalid * 2,
+                              &full[slot]);
+        }
       };
       const int prefill = min(n_units, S);
       // weights do not depend on the previous kernel: start streaming them before the PDL wait
@@ -194,6 +221,7 @@ __global__ void __launch_bounds__(kThreads)
 
   // =========================== consumers ===========================
   ptx::pdl_wait_prior_grid();
+  if (threadIdx.x == 0) stamp(p, 2);
   const int g = lane >> 2, tig = lane & 3;
   constexpr int NT = kM1 ? 2 : 4;  // accumulator registers kept per MMA tile
   float tot[8][NT];
@@ -207,9 +235,10 @@ __global__ void __launch_bounds__(kThreads)
   int tile = u0 / p.SPT, ks = u0 - tile * p.SPT;  // tracked incrementally (no division in the loop)
   for (int it = 0; it < n_units; ++it) {
     ptx::mbar_wait(&full[slot], phase);
+    if (it == 0 && threadIdx.x == 0) stamp(p, 3);
     const uint32_t wrow = Wsm + slot * W_BYTES + (16 * warp) * BN;
     const uint32_t srow = Ssm + slot * S_BYTES + warp * (BN * 2) + g * 32;
-    const uint32_t arow = Asm + slot * A_BYTES + g * A_STRIDE + (32 * warp + 4 * tig) * 2;
+    const uint32_t arow = Asm + slot * C::A_BYTES + (kM1 ? 0 : g * A_STRIDE) + (32 * warp + 4 * tig) * 2;
 
     float grp[8][4];
     float ag[4];
@@ -290,6 +319,7 @@ __global__ void __launch_bounds__(kThreads)
 
     // ---------------- end of a column tile (or of this CTA's range): reduce and emit
     if (ks == p.SPT - 1 || it == n_units - 1) {
+      if (it == n_units - 1 && threadIdx.x == 0) stamp(p, 4);
       // (1) cross-warp (k-group) reduction through shared memory
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -298,20 +328,20 @@ __global__ void __launch_bounds__(kThreads)
           const int tok = kM1 ? 0 : 2 * tig + (i & 1);
           const int col = 16 * g + 2 * j + (kM1 ? i : (i >> 1));
           const bool ok = kM1 ? (tig == 0) : (tok < p.M);
-          if (ok) red[(warp * MMAX + tok) * BN + col] = tot[j][i];
+          if (ok) red[(warp * MR + tok) * BN + col] = tot[j][i];
           tot[j][i] = 0.f;
         }
       }
       ptx::named_bar_sync(1, CW * 32);
       const int t = threadIdx.x;  // column within the tile
       const int n = tile * BN + t;
-      float v[MMAX];
+      float v[MR];
 #pragma unroll
-      for (int m = 0; m < MMAX; ++m) {
+      for (int m = 0; m < MR; ++m) {
         v[m] = 0.f;
         if (m < p.M) {
 #pragma unroll
-          for (int w = 0; w < CW; ++w) v[m] += red[(w * MMAX + m) * BN + t];
+          for (int w = 0; w < CW; ++w) v[m] += red[(w * MR + m) * BN + t];
         }
       }
       // (2) is the tile cut by a range boundary?
@@ -322,37 +352,56 @@ __global__ void __launch_bounds__(kThreads)
         const int my_slot = c * 2 + ((tile == u0 / p.SPT) ? 0 : 1);
         float* mine = p.partials + static_cast<size_t>(my_slot) * kSlotFloats;
 #pragma unroll
-        for (int m = 0; m < MMAX; ++m)
+        for (int m = 0; m < MR; ++m)
           if (m < p.M) mine[m * BN + t] = v[m];
-        __threadfence();
-        ptx::named_bar_sync(1, CW * 32);
+        ptx::named_bar_sync(1, CW * 32);  // every partial of this CTA is issued ...
         const int c_first = unit_owner(p.U, P, t_first), c_last = unit_owner(p.U, P, t_last);
         if (t == 0) {
-          const int old = atomicAdd(&p.counters[tile], 1);
+          ptx::fence_acq_rel_gpu();       // ... and made visible (cumulative) before the count
+          const int old = atomicAdd(&p.counters[tile * kCounterStride], 1);
           const int last = (old == c_last - c_first) ? 1 : 0;
-          if (last) p.counters[tile] = 0;  // self-cleaning: every contributor has arrived
+          if (last) {
+            p.counters[tile * kCounterStride] = 0;         // self-cleaning: every contributor has arrived
+            ptx::fence_acq_rel_gpu();     // acquire side: the others' partials are visible
+          }
           *flag = last;
+          if (it == n_units - 1) stamp(p, 6);
         }
         ptx::named_bar_sync(1, CW * 32);
         write_out = (*flag != 0);
         if (write_out) {
-          __threadfence();
+          // Contributor cc > c_first starts inside this tile (its first tile -> slot 0); c_first
+          // uses slot 1 iff its range began in an earlier tile.
+          const int first_slot = (unit_begin(p.U, P, c_first) < t_first) ? 1 : 0;
 #pragma unroll
-          for (int m = 0; m < MMAX; ++m) v[m] = 0.f;
-          for (int cc = c_first; cc <= c_last; ++cc) {  // fixed order -> deterministic sum
-            const int sl = cc * 2 + ((tile == unit_begin(p.U, P, cc) / p.SPT) ? 0 : 1);
-            const float* src = p.partials + static_cast<size_t>(sl) * kSlotFloats;
+          for (int m = 0; m < MR; ++m) v[m] = 0.f;
+          // fixed order -> deterministic sum; loads are issued in batches so that their L2
+          // latencies overlap instead of adding up (the tile has up to ~10 contributors)
+          constexpr int CH = kM1 ? 8 : 2;
+          for (int cb = c_first; cb <= c_last; cb += CH) {
+            float ld[CH][MR];
 #pragma unroll
-            for (int m = 0; m < MMAX; ++m)
-              if (m < p.M) v[m] += ptx::ldcg_f32(src + m * BN + t);
+            for (int i = 0; i < CH; ++i) {
+              const int cc = cb + i;
+              const int sl = cc * 2 + (cc == c_first ? first_slot : 0);
+              const float* src = p.partials + static_cast<size_t>(sl) * kSlotFloats;
+#pragma unroll
+              for (int m = 0; m < MR; ++m)
+                ld[i][m] = (cc <= c_last && m < p.M) ? ptx::ldcg_f32(src + m * BN + t) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+#pragma unroll
+              for (int m = 0; m < MR; ++m) v[m] += ld[i][m];
           }
+          if (t == 0) stamp(p, 7);
         }
       }
       if (write_out && n < p.N) {
         T* Cp = static_cast<T*>(p.C);
         const T* bias = static_cast<const T*>(p.bias);
 #pragma unroll
-        for (int m = 0; m < MMAX; ++m)
+        for (int m = 0; m < MR; ++m)
           if (m < p.M) Cp[m * p.ldc + n] = epilogue<T>(v[m], bias, n);
       }
       ptx::named_bar_sync(1, CW * 32);  // red[] / flag may be reused
@@ -362,6 +411,7 @@ __global__ void __launch_bounds__(kThreads)
       ++tile;
     }
   }
+  if (threadIdx.x == 0) stamp(p, 5);
 }
 
 int env_int(const char* name, int dflt, int lo, int hi) {
@@ -375,7 +425,10 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 
 template <typename T, bool kTrick, bool kM1>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
-                int grid, size_t smem, bool pdl) {
+                int grid, int stages, bool pdl) {
+  using C = Cfg<kM1>;
+  const size_t smem =
+      1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES + 16 * stages + 16;
   auto kern = w4_gemv_kernel<T, kTrick, kM1>;
   static size_t configured[64] = {0};
   int dev = 0;
@@ -405,7 +458,7 @@ int launch_t(const GemmArgs& a, bool exact) {
   const int SPT = (G + CW - 1) / CW;
   const int tiles = (a.N + BN - 1) / BN;
   const int U = tiles * SPT;
-  static const int stages = env_int("CGQ_GEMV_STAGES", 8, 2, 16);
+  static const int stages = env_int("CGQ_GEMV_STAGES", 4, 2, 16);
   static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 2, 1, 4);
   static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
   int grid = sm_count() * cps;
@@ -440,17 +493,16 @@ int launch_t(const GemmArgs& a, bool exact) {
   prm.S = stages;
   prm.counters = static_cast<int*>(a.workspace);
   prm.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kCounterBytes);
-  const size_t smem =
-      1024 + static_cast<size_t>(stages) * (W_BYTES + S_BYTES + A_BYTES) + RED_BYTES + 16 * stages + 16;
+  prm.trace = static_cast<unsigned long long*>(take_trace_buffer());
 
   constexpr bool kIsHalf = (DT<T>::code == CGQ_DTYPE_F16);
   const bool trick = kIsHalf && !exact;
   if (a.M == 1) {
-    if (trick) return launch_inst<T, kIsHalf, true>(a, tmW, tmS, prm, grid, smem, pdl);
-    return launch_inst<T, false, true>(a, tmW, tmS, prm, grid, smem, pdl);
+    if (trick) return launch_inst<T, kIsHalf, true>(a, tmW, tmS, prm, grid, stages, pdl);
+    return launch_inst<T, false, true>(a, tmW, tmS, prm, grid, stages, pdl);
   }
-  if (trick) return launch_inst<T, kIsHalf, false>(a, tmW, tmS, prm, grid, smem, pdl);
-  return launch_inst<T, false, false>(a, tmW, tmS, prm, grid, smem, pdl);
+  if (trick) return launch_inst<T, kIsHalf, false>(a, tmW, tmS, prm, grid, stages, pdl);
+  return launch_inst<T, false, false>(a, tmW, tmS, prm, grid, stages, pdl);
 }
 
 }  // namespace

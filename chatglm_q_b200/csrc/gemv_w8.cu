@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(kThreads)
         ptx::named_bar_sync(1, CW * 32);
         const int c_first = unit_owner(p.U, P, t_first), c_last = unit_owner(p.U, P, t_last);
         if (t == 0) {
-          const int old = atomicAdd(&p.counters[tile], 1);
+          const int old = atomicAdd(&p.counters[tile * kCounterStride], 1);
           const int last = (old == c_last - c_first) ? 1 : 0;
-          if (last) p.counters[tile] = 0;
+          if (last) p.counters[tile * kCounterStride] = 0;
           *flag = last;
         }
         ptx::named_bar_sync(1, CW * 32);

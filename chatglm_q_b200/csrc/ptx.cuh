@@ -50,6 +50,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// gpu-scope acquire/release fence (cheaper than __threadfence(), which is fence.sc)
+__device__ __forceinline__ void fence_acq_rel_gpu() {
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- L2 cache policies
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;

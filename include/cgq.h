@@ -125,6 +125,15 @@ int cgq_w4_embedding(const int64_t* ids, int n_ids, const uint8_t* Wq /*[V/2, D]
 int cgq_w8_embedding(const int64_t* ids, int n_ids, const int8_t* Wq /*[V, D]*/,
                      const void* scale /*[D]*/, void* out, int V, int D, int dtype, void* stream);
 
+/*
+ * Profiling aid (no reference counterpart): the NEXT decode-kernel launch issued by the calling
+ * thread writes a per-CTA timeline (8 x uint64 %globaltimer stamps per CTA, first 1024 CTAs:
+ * entry, producer start, consumer dependency wait passed, first data, loop end, exit,
+ * producer prefetch issued, producer done) into `device_buffer` (>= 64 KiB, zeroed by the
+ * caller).  One-shot: the pointer is consumed by that launch.  NULL cancels.
+ */
+void cgq_debug_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

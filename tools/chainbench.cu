@@ -1,0 +1,249 @@
+// chainbench — standalone (no torch, no python) timing harness for the decode path through the
+// C-ABI (include/cgq.h).  Development tool; bench.py is the judged measurement.
+//
+//   chainbench chain  [M] [reps]            ChatGLM2-6B token step: 28 x (qkv,o,w_in,w_out) + lm_head
+//   chainbench single K N [M] [reps]        one shape, weights rotated over > L2 worth of copies
+//   chainbench trace  [M]                   chain once with the in-kernel timeline (cgq_debug_trace)
+//
+// Weights are random bytes (nibbles 1..15), scales ~ 1/(4.4*sqrt(K)) so the chain stays finite.
+// Every timing is CUDA events around `reps` replays of a CUDA graph of the launches.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../include/cgq.h"
+
+#define CK(x)                                                                  \
+  do {                                                                         \
+    cudaError_t e_ = (x);                                                      \
+    if (e_ != cudaSuccess) {                                                   \
+      fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      exit(1);                                                                 \
+    }                                                                          \
+  } while (0)
+#define CG(x)                                                             \
+  do {                                                                    \
+    int r_ = (x);                                                         \
+    if (r_ != 0) {                                                        \
+      fprintf(stderr, "%s:%d %s -> %d: %s\n", __FILE__, __LINE__, #x, r_, cgq_last_error()); \
+      exit(1);                                                            \
+    }                                                                     \
+  } while (0)
+
+__global__ void fill_w4(uint8_t* w, size_t n, uint32_t seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    uint32_t lo = 1 + (x % 15), hi = 1 + ((x >> 8) % 15);
+    w[i] = (uint8_t)(lo | (hi << 4));
+  }
+}
+__global__ void fill_w8(int8_t* w, size_t n, uint32_t seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    w[i] = (int8_t)((int)(x % 255) - 127);
+  }
+}
+__global__ void fill_h(__half* s, size_t n, uint32_t seed, float lo, float hi) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    s[i] = __float2half(lo + (hi - lo) * ((x & 0xFFFF) / 65535.f));
+  }
+}
+
+struct Lin {
+  int K, N;
+  bool bias;
+  uint8_t* w;
+  __half* s;
+  __half* b;
+  size_t bytes(int M) const {
+    return (size_t)K * N / 2 + (size_t)(K / 32) * N * 2 + (size_t)M * K * 2 + (size_t)M * N * 2 +
+           (bias ? (size_t)N * 2 : 0);
+  }
+};
+
+static Lin make_lin(int K, int N, bool bias, uint32_t seed) {
+  Lin l{K, N, bias, nullptr, nullptr, nullptr};
+  CK(cudaMalloc(&l.w, (size_t)K / 2 * N));
+  CK(cudaMalloc(&l.s, (size_t)(K / 32) * N * 2));
+  fill_w4<<<1184, 256>>>(l.w, (size_t)K / 2 * N, seed);
+  float sc = 1.f / (4.4f * sqrtf((float)K));
+  fill_h<<<592, 256>>>(l.s, (size_t)(K / 32) * N, seed + 1, 0.75f * sc, 1.25f * sc);
+  if (bias) {
+    CK(cudaMalloc(&l.b, (size_t)N * 2));
+    fill_h<<<64, 256>>>(l.b, N, seed + 2, -0.02f, 0.02f);
+  }
+  return l;
+}
+
+static void* g_ws;
+static size_t g_ws_bytes;
+
+static void run_lin(const Lin& l, const __half* x, __half* y, int M, int lda, cudaStream_t st) {
+  CG(cgq_w4a16_gemm(x, lda, l.w, l.s, l.b, y, l.N, M, l.N, l.K, 32, CGQ_DTYPE_F16, g_ws, g_ws_bytes,
+                    st));
+}
+
+static float time_graph(cudaGraphExec_t ge, cudaStream_t st, int reps) {
+  for (int i = 0; i < 3; ++i) CK(cudaGraphLaunch(ge, st));
+  CK(cudaStreamSynchronize(st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; ++i) CK(cudaGraphLaunch(ge, st));
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms / reps;
+}
+
+int main(int argc, char** argv) {
+  const char* mode = argc > 1 ? argv[1] : "chain";
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  g_ws_bytes = cgq_workspace_bytes();
+  CK(cudaMalloc(&g_ws, g_ws_bytes));
+  CK(cudaMemset(g_ws, 0, g_ws_bytes));
+  const int H = 4096, INNER = 13696, VOCAB = 65024, QKV = 4608, LAYERS = 28;
+
+  if (!strcmp(mode, "single")) {
+    int K = atoi(argv[2]), N = atoi(argv[3]);
+    int M = argc > 4 ? atoi(argv[4]) : 1;
+    int reps = argc > 5 ? atoi(argv[5]) : 20;
+    size_t per = (size_t)K * N / 2 + (size_t)(K / 32) * N * 2;
+    int copies = (int)std::max<size_t>(2, (400u << 20) / per + 1);
+    if (M > 8) copies = std::min(copies, 4);
+    std::vector<Lin> ls;
+    for (int i = 0; i < copies; ++i) ls.push_back(make_lin(K, N, false, 77 + 3 * i));
+    __half *x, *y;
+    CK(cudaMalloc(&x, (size_t)M * K * 2));
+    CK(cudaMalloc(&y, (size_t)M * N * 2));
+    fill_h<<<64, 256>>>(x, (size_t)M * K, 5, -1.f, 1.f);
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < copies; ++i) run_lin(ls[i], x, y, M, K, st);
+    CK(cudaStreamSynchronize(st));
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < copies; ++i) run_lin(ls[i], x, y, M, K, st);
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    float ms = time_graph(ge, st, reps);
+    double us = ms * 1e3 / copies;
+    double by = (double)ls[0].bytes(M), fl = 2.0 * M * N * (double)K;
+    printf("single M=%d K=%d N=%d copies=%d: %.2f us/launch  %.1f GB/s  %.2f TFLOP/s\n", M, K, N,
+           copies, us, by / us / 1e3, fl / us / 1e6);
+    return 0;
+  }
+
+  // ---- chain
+  int M = argc > 2 ? atoi(argv[2]) : 1;
+  int reps = argc > 3 ? atoi(argv[3]) : 20;
+  std::vector<Lin> ls;
+  size_t total = 0;
+  for (int l = 0; l < LAYERS; ++l) {
+    ls.push_back(make_lin(H, QKV, true, 1000 + 16 * l));
+    ls.push_back(make_lin(H, H, false, 1001 + 16 * l));
+    ls.push_back(make_lin(H, 2 * INNER, false, 1002 + 16 * l));
+    ls.push_back(make_lin(INNER, H, false, 1003 + 16 * l));
+  }
+  ls.push_back(make_lin(H, VOCAB, false, 9));
+  for (auto& l : ls) total += l.bytes(M);
+  __half *x, *b0, *b1, *b2, *b3, *logits;
+  CK(cudaMalloc(&x, (size_t)M * H * 2));
+  CK(cudaMalloc(&b0, (size_t)M * QKV * 2));
+  CK(cudaMalloc(&b1, (size_t)M * H * 2));
+  CK(cudaMalloc(&b2, (size_t)M * 2 * INNER * 2));
+  CK(cudaMalloc(&b3, (size_t)M * H * 2));
+  CK(cudaMalloc(&logits, (size_t)M * VOCAB * 2));
+  fill_h<<<64, 256>>>(x, (size_t)M * H, 5, -1.f, 1.f);
+  CK(cudaDeviceSynchronize());
+
+  uint64_t* trace = nullptr;
+  const int kTraceWords = 8, kTraceCtas = 1024;
+  const bool tracing = !strcmp(mode, "trace");
+  if (tracing) {
+    CK(cudaMalloc(&trace, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+    CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+  }
+  auto chain = [&]() {
+    const __half* cur = x;
+    for (int l = 0; l < LAYERS; ++l) {
+      const Lin* p = &ls[4 * l];
+      if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 0) * kTraceWords * kTraceCtas);
+      run_lin(p[0], cur, b0, M, H, st);
+      if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 1) * kTraceWords * kTraceCtas);
+      run_lin(p[1], b0, b1, M, QKV, st);  // attention stand-in: first 4096 columns of qkv
+      if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 2) * kTraceWords * kTraceCtas);
+      run_lin(p[2], b1, b2, M, H, st);
+      if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 3) * kTraceWords * kTraceCtas);
+      run_lin(p[3], b2, b3, M, 2 * INNER, st);  // silu*gate stand-in: first 13696 columns
+      cur = b3;
+    }
+    if (tracing) cgq_debug_trace(trace + (size_t)(4 * LAYERS) * kTraceWords * kTraceCtas);
+    run_lin(ls.back(), cur, logits, M, H, st);
+  };
+  chain();
+  CK(cudaStreamSynchronize(st));
+  if (tracing) {
+    CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+    chain();  // second (warm) pass is the one reported
+    CK(cudaStreamSynchronize(st));
+    std::vector<uint64_t> h(kTraceWords * kTraceCtas * ls.size());
+    CK(cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost));
+    uint64_t t00 = ~0ull;
+    for (size_t i = 0; i < h.size(); i += kTraceWords)
+      if (h[i]) t00 = std::min(t00, h[i]);
+    const char* names[8] = {"entry", "prolog", "depwait", "firstdata", "loopend", "exit", "fix_atomic", "fix_loaded"};
+    for (size_t k = 0; k < std::min<size_t>(ls.size(), 9); ++k) {
+      printf("kernel %zu (K=%d N=%d):\n", k, ls[k].K, ls[k].N);
+      for (int w = 0; w < kTraceWords; ++w) {
+        uint64_t mn = ~0ull, mx = 0;
+        double sum = 0;
+        int cnt = 0;
+        for (int c = 0; c < kTraceCtas; ++c) {
+          uint64_t v = h[(k * kTraceCtas + c) * kTraceWords + w];
+          if (!v) continue;
+          mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)(v - t00); ++cnt;
+        }
+        if (cnt)
+          printf("  %-10s n=%4d  min %8.2f  avg %8.2f  max %8.2f us\n", names[w], cnt,
+                 (mn - t00) / 1e3, sum / cnt / 1e3, (mx - t00) / 1e3);
+      }
+    }
+    return 0;
+  }
+  cudaGraph_t g;
+  cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  chain();
+  CK(cudaStreamEndCapture(st, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  float ms = time_graph(ge, st, reps);
+  printf("chain M=%d: %.1f us/token  %.1f tok/s  %.1f GB/s algorithmic (%.3f GB)  %.2f us/launch\n", M,
+         ms * 1e3, 1e3 / ms, total / (ms * 1e-3) / 1e9, total / 1e9, ms * 1e3 / ls.size());
+  // no-graph stream launches, for comparison
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; ++i) chain();
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("chain M=%d stream launches (no graph): %.1f us/token\n", M, ms * 1e3 / reps);
+  return 0;
+}
