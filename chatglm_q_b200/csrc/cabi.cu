@@ -203,12 +203,20 @@ extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, 
   if (impl == CGQ_IMPL_AUTO) {
     if (M <= 8 && w4_gemv_supported(a) && workspace != nullptr && workspace_bytes >= kWorkspaceBytes)
       impl = CGQ_IMPL_GEMV;
+    else if (M > 8 && w4_tc_supported(a))
+      impl = CGQ_IMPL_TC;
     else
       impl = CGQ_IMPL_SIMPLE;
   }
   switch (impl) {
     case CGQ_IMPL_SIMPLE:
       return launch_w4_simple(a);
+    case CGQ_IMPL_TC:
+      if (!w4_tc_supported(a)) {
+        set_error("%s: tcgen05 kernel needs K%%32==0, N%%16==0, 16-byte aligned pointers, lda%%8==0", fn);
+        return CGQ_ERR_MISALIGNED;
+      }
+      return launch_w4_tc(a);
     case CGQ_IMPL_GEMV:
     case CGQ_IMPL_GEMV_EXACT:
       if (M > 8 || !w4_gemv_supported(a)) {

@@ -91,6 +91,8 @@ int launch_w4_simple(const GemmArgs& a);
 int launch_w8_simple(const GemmArgs& a);
 int launch_w4_gemv(const GemmArgs& a, bool exact);
 int launch_w8_gemv(const GemmArgs& a);
+int launch_w4_tc(const GemmArgs& a);
+bool w4_tc_supported(const GemmArgs& a);
 bool w4_gemv_supported(const GemmArgs& a);
 bool w8_gemv_supported(const GemmArgs& a);
 

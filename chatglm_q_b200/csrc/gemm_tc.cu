@@ -1,0 +1,390 @@
+// int4g32 prefill kernel (M > 8): C[M,N] = A[M,K] · ((nib(Wq) - 8) * scale), tcgen05 + TMEM.
+// Replaces _dynamic_quant_matmul_s4_kernel (chatglm_q/int4/triton_ops.py:18-87) for prefill, where
+// the reference re-reads and re-dequantises the whole weight for every 16-row block of A.
+//
+// The product is computed TRANSPOSED on the 5th-generation tensor cores:
+//     D[n, m] = Σ_k  Wdq^T[n, k] · A^T[k, m]          (UMMA  M = 128 weight columns, N = MB tokens, K = 16)
+// so that
+//   * the dequantised weight tile — N-contiguous in memory, exactly like the packed tensor — is the
+//     MN-major A operand (no transpose anywhere), and
+//   * the activation tile [tokens x 64 k] (K-contiguous rows of A) is the K-major B operand, TMA-loaded
+//     with the 128-byte swizzle straight into its canonical UMMA layout; any token count > 8 maps to
+//     MB in {32, 64, 128, 256} without padding the 128-wide UMMA M.
+//
+// Warp roles (320 threads, persistent over (n-tile, token-block) tiles, weights of one n-tile are
+// shared through L2 by the CTAs working on its token blocks at the same time):
+//   warp 8      TMA producer: packed weights [32 x 128 B], scales [2 x 128], activations [MB x 64]
+//   warps 4-7   dequant: packed smem -> registers -> fp16/bf16 tile in the canonical MN-major
+//               SWIZZLE_128B layout (reference rounding: (q-8) exact, one rounding in the multiply by
+//               the group scale), fence.proxy.async, mbarrier
+//   warp 9      one lane issues tcgen05.mma (cta_group::1, kind::f16, fp32 accumulators in TMEM),
+//               tcgen05.commit releases the smem stages; owns the TMEM allocation (2 accumulators)
+//   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 bit) -> round to T -> (+ bias, second rounding)
+//               -> C, overlapped with the next tile's MMAs through the second accumulator
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace cgq {
+namespace {
+
+constexpr int TN = 128;          // weight columns per tile  (UMMA M)
+constexpr int BK = 64;           // k per pipeline stage      (4 UMMA K-steps)
+constexpr int STAGES = 4;        // TMA ring depth
+constexpr int ABUFS = 2;         // dequantised-A double buffer
+constexpr int kThreads = 320;
+constexpr int P_BYTES = (BK / 2) * TN;       // 4096: packed tile
+constexpr int S_BYTES = (BK / 32) * TN * 2;  // 512: scale tile
+constexpr int PS_BYTES = 5120;               // packed + scales, padded to keep B tiles 1024-aligned
+constexpr int A_BYTES = TN * BK * 2;         // 16384: dequantised tile
+constexpr int ATOM = 1024;                   // 8 rows x 128 B swizzle atom
+
+struct Params {
+  const void* bias;
+  void* C;
+  int64_t ldc;
+  int M, N, K;
+  int MB;        // tokens per tile (UMMA N)
+  int n_tiles, m_blocks, k_stages;
+  uint32_t idesc;
+};
+
+// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) |
+         (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+// One 32-bit word = 4 packed bytes = columns (c0, c1, c2, c3) of one packed row (k = 2r, 2r+1).
+// Produces round_T((q - 8) * s) for the column PAIRS (c0, c2) and (c1, c3) of both k values;
+// s02 / s13 hold the matching scale pairs.  Bit-exact with chatglm_q/int4/qlinear.py:29-32.
+template <typename T>
+struct Deq;
+template <>
+struct Deq<__half> {
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t s02, uint32_t s13, uint32_t& e02,
+                                             uint32_t& e13, uint32_t& o02, uint32_t& o13) {
+    const uint32_t w8 = w >> 8;
+    e02 = h2_mul(h2_sub(ptx::and_or(w, 0x000F000Fu, 0x64006400u), 0x64086408u), s02);   // (1024+q)-1032
+    e13 = h2_mul(h2_sub(ptx::and_or(w8, 0x000F000Fu, 0x64006400u), 0x64086408u), s13);
+    o02 = h2_mul(h2_fma(ptx::and_or(w, 0x00F000F0u, 0x64006400u), 0x2C002C00u, 0xD480D480u), s02);  // (1024+16q)/16-72
+    o13 = h2_mul(h2_fma(ptx::and_or(w8, 0x00F000F0u, 0x64006400u), 0x2C002C00u, 0xD480D480u), s13);
+  }
+};
+template <>
+struct Deq<__nv_bfloat16> {
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t s02, uint32_t s13, uint32_t& e02,
+                                             uint32_t& e13, uint32_t& o02, uint32_t& o13) {
+    // bf16 keeps 8 significant bits: 128 + q is exact, the high nibble is shifted down first
+    e02 = bf2_mul(bf2_sub(ptx::and_or(w, 0x000F000Fu, 0x43004300u), 0x43084308u), s02);  // (128+q)-136
+    e13 = bf2_mul(bf2_sub(ptx::and_or(w >> 8, 0x000F000Fu, 0x43004300u), 0x43084308u), s13);
+    o02 = bf2_mul(bf2_sub(ptx::and_or(w >> 4, 0x000F000Fu, 0x43004300u), 0x43084308u), s02);
+    o13 = bf2_mul(bf2_sub(ptx::and_or(w >> 12, 0x000F000Fu, 0x43004300u), 0x43084308u), s13);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+    w4_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmS,
+                      const __grid_constant__ CUtensorMap tmA, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int MB = p.MB;
+  const uint32_t b_bytes = static_cast<uint32_t>(MB) * 128u;   // [MB tokens x 64 k] 16-bit
+  const uint32_t stage_bytes = b_bytes + PS_BYTES;
+  // layout: A buffers | stages { B tile | packed | scales } | barriers | tmem ptr
+  const uint32_t off_stage = ABUFS * A_BYTES;
+  const uint32_t off_bar = off_stage + STAGES * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + off_bar);
+  uint64_t* full_tma = bars;                    // [STAGES]
+  uint64_t* empty_tma = full_tma + STAGES;      // [STAGES]
+  uint64_t* a_full = empty_tma + STAGES;        // [ABUFS]
+  uint64_t* a_empty = a_full + ABUFS;           // [ABUFS]
+  uint64_t* acc_full = a_empty + ABUFS;         // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles * p.m_blocks;
+  const uint32_t tmem_cols = (2 * MB <= 32) ? 32u : (2 * MB <= 64) ? 64u : (2 * MB <= 128) ? 128u
+                             : (2 * MB <= 256) ? 256u : 512u;
+
+  if (threadIdx.x == 8 * 32) {
+    ptx::prefetch_tmap(&tmP);
+    ptx::prefetch_tmap(&tmS);
+    ptx::prefetch_tmap(&tmA);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_tma[s], 1);
+      ptx::mbar_init(&empty_tma[s], 1);
+    }
+    for (int b = 0; b < ABUFS; ++b) {
+      ptx::mbar_init(&a_full[b], 4);
+      ptx::mbar_init(&a_empty[b], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) {
+    ptx::tmem_alloc(tmem_slot, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      const uint64_t pol_w = ptx::policy_evict_first();   // weights: streamed (re-use is in L2 window)
+      const uint64_t pol_a = ptx::policy_evict_last();    // activations: re-read by every n-tile
+      int s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / p.m_blocks, mb = tile - nt * p.m_blocks;
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          ptx::mbar_wait(&empty_tma[s], ph ^ 1);
+          uint8_t* st = gen + off_stage + s * stage_bytes;
+          ptx::mbar_expect_tx(&full_tma[s], b_bytes + P_BYTES + S_BYTES);
+          ptx::tma_load_2d(st, &tmA, ks * BK, mb * MB, &full_tma[s], pol_a);
+          ptx::tma_load_2d(st + b_bytes, &tmP, nt * TN, ks * (BK / 2), &full_tma[s], pol_w);
+          ptx::tma_load_2d(st + b_bytes + P_BYTES, &tmS, nt * TN, ks * (BK / 32), &full_tma[s], pol_w);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int s = 0, ph = 0, ab = 0, aph = 0, acc = 0, cph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&acc_empty[acc], cph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB);
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          ptx::mbar_wait(&full_tma[s], ph);
+          ptx::mbar_wait(&a_full[ab], aph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = base + ab * A_BYTES;
+          const uint32_t b_addr = base + off_stage + s * stage_bytes;
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            // A: MN-major, 64-column halves 8 KB apart (LBO), 8-k atoms 1 KB apart (SBO)
+            const uint64_t adesc = make_desc(a_addr + k4 * 2 * ATOM, (BK / 8) * ATOM, ATOM);
+            // B: K-major rows of 128 B, 8-row atoms 1 KB apart; K-step = 32 B inside the row
+            const uint64_t bdesc = make_desc(b_addr + k4 * 32, 16, ATOM);
+            ptx::umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (ks | k4) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_tma[s]);   // stage (activations + packed) reusable when MMAs retire
+          ptx::umma_commit(&a_empty[ab]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+          if (++ab == ABUFS) {
+            ab = 0;
+            aph ^= 1;
+          }
+        }
+        ptx::umma_commit(&acc_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          cph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== dequant warps =====================================
+    // thread -> (16-byte output chunk c of 8 columns, packed rows r0 + 8 i); 128 threads cover
+    // 32 packed rows x 16 chunks.  Chunk element order is (c0,c2,c1,c3,c4,c6,c5,c7): the epilogue
+    // un-permutes the TMEM lanes.
+    const int t = threadIdx.x - 128;
+    const int c = t & 15;          // column chunk: columns 8c .. 8c+7
+    const int r0 = t >> 4;         // 0..7
+    int s = 0, ph = 0, ab = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int ks = 0; ks < p.k_stages; ++ks) {
+        ptx::mbar_wait(&full_tma[s], ph);
+        const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
+        uint32_t out[4][8];  // [row i][k parity * 4 + word]
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint4 sv = ptx::lds128(st + P_BYTES + g * (TN * 2) + c * 16);
+          const uint32_t s02a = __byte_perm(sv.x, sv.y, 0x5410), s13a = __byte_perm(sv.x, sv.y, 0x7632);
+          const uint32_t s02b = __byte_perm(sv.z, sv.w, 0x5410), s13b = __byte_perm(sv.z, sv.w, 0x7632);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = 2 * g + h;                 // packed row r0 + 8 i  (rows 0..15 = group 0)
+            const uint2 pk = ptx::lds64(st + (r0 + 8 * i) * TN + c * 8);
+            Deq<T>::run(pk.x, s02a, s13a, out[i][0], out[i][1], out[i][4], out[i][5]);
+            Deq<T>::run(pk.y, s02b, s13b, out[i][2], out[i][3], out[i][6], out[i][7]);
+          }
+        }
+        ptx::mbar_wait(&a_empty[ab], aph ^ 1);
+        const uint32_t a_addr = base + ab * A_BYTES + (c >> 3) * ((BK / 8) * ATOM);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const int k = 2 * (r0 + 8 * i) + par;    // k row inside the stage
+            const uint32_t addr = a_addr + (k >> 3) * ATOM + (k & 7) * 128 + (((c & 7) ^ (k & 7)) << 4);
+            ptx::sts128(addr, make_uint4(out[i][4 * par], out[i][4 * par + 1], out[i][4 * par + 2],
+                                         out[i][4 * par + 3]));
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+        if (++ab == ABUFS) {
+          ab = 0;
+          aph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps =====================================
+    T* Cp = static_cast<T*>(p.C);
+    const T* bias = static_cast<const T*>(p.bias);
+    const int row = warp * 32 + lane;                       // TMEM lane = permuted column of the tile
+    const int col_in_tile = (row & ~3) | ((row & 1) << 1) | ((row >> 1) & 1);   // (0,2,1,3) un-permute
+    int acc = 0, cph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile / p.m_blocks, mb = tile - nt * p.m_blocks;
+      const int n = nt * TN + col_in_tile;
+      const int m0 = mb * MB;
+      ptx::mbar_wait(&acc_full[acc], cph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) +
+                             static_cast<uint32_t>(acc * MB);
+      for (int c0 = 0; c0 < MB; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < p.M) Cp[static_cast<int64_t>(m) * p.ldc + n] = epilogue<T>(__uint_as_float(v[j]), bias, n);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        cph ^= 1;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+template <typename T>
+int launch_t(const GemmArgs& a) {
+  const int MB = a.M > 128 ? 256 : a.M > 64 ? 128 : a.M > 32 ? 64 : 32;
+  Params prm;
+  prm.bias = a.bias;
+  prm.C = a.C;
+  prm.ldc = a.ldc;
+  prm.M = a.M;
+  prm.N = a.N;
+  prm.K = a.K;
+  prm.MB = MB;
+  prm.n_tiles = (a.N + TN - 1) / TN;
+  prm.m_blocks = (a.M + MB - 1) / MB;
+  prm.k_stages = (a.K + BK - 1) / BK;
+  const uint32_t fmt = (DT<T>::code == CGQ_DTYPE_F16) ? 0u : 1u;
+  // c=F32 | a,b format | A MN-major | B K-major | N = MB | M = 128
+  prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) |
+              (static_cast<uint32_t>(MB >> 3) << 17) | (static_cast<uint32_t>(TN >> 4) << 24);
+
+  const CUtensorMapDataType dt16 = (DT<T>::code == CGQ_DTYPE_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmP, tmS, tmA;
+  TmapKey kp{a.Wq, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 2),
+             static_cast<uint64_t>(a.N), TN, BK / 2, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+             CU_TENSOR_MAP_SWIZZLE_NONE};
+  int rc = get_tmap_2d(kp, &tmP);
+  if (rc != CGQ_OK) return rc;
+  TmapKey ks{a.scale, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 32),
+             static_cast<uint64_t>(a.N) * 2, TN, BK / 32, dt16, CU_TENSOR_MAP_SWIZZLE_NONE};
+  rc = get_tmap_2d(ks, &tmS);
+  if (rc != CGQ_OK) return rc;
+  TmapKey ka{a.A, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M),
+             static_cast<uint64_t>(a.lda) * 2, BK, static_cast<uint32_t>(MB), dt16,
+             CU_TENSOR_MAP_SWIZZLE_128B};
+  rc = get_tmap_2d(ka, &tmA);
+  if (rc != CGQ_OK) return rc;
+
+  const size_t smem = 1024 + ABUFS * A_BYTES + static_cast<size_t>(STAGES) * (MB * 128 + PS_BYTES) +
+                      8 * (2 * STAGES + 2 * ABUFS + 4) + 16;
+  auto kern = w4_gemm_tc_kernel<T>;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CGQ_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    configured[dev] = smem;
+  }
+  int grid = prm.n_tiles * prm.m_blocks;
+  if (grid > sm_count()) grid = sm_count();
+  kern<<<grid, kThreads, smem, a.stream>>>(tmP, tmS, tmA, prm);
+  CGQ_CUDA_TRY(cudaGetLastError());
+  return CGQ_OK;
+}
+
+}  // namespace
+
+bool w4_tc_supported(const GemmArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return a.M >= 1 && a.K % 32 == 0 && a.N % 16 == 0 && al16(a.Wq) && al16(a.scale) && al16(a.A) &&
+         a.lda % 8 == 0;
+}
+
+int launch_w4_tc(const GemmArgs& a) {
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a) : launch_t<__nv_bfloat16>(a);
+}
+
+}  // namespace cgq

@@ -21,7 +21,7 @@ from chatglm_q_b200 import ops  # noqa: E402
 
 DEV = "cuda"
 IMPLS4 = {"auto": ops.IMPL_AUTO, "simple": ops.IMPL_SIMPLE, "gemv": ops.IMPL_GEMV,
-          "gemv_exact": ops.IMPL_GEMV_EXACT}
+          "gemv_exact": ops.IMPL_GEMV_EXACT, "tc": ops.IMPL_TC}
 
 
 def u8(x):
@@ -171,6 +171,33 @@ def test_int8_prefill_m(m):
     k, n = 4096, 768
     a, q, s = make_int8_case(78 + m, m, k, n, "Q")
     assert_parity(run8(a, q, s, "float16"), c_oracle.w8a16_gemm(a, q, s, None, "float16"), f"int8 M={m}")
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("kind", ["Q", "R"])
+def test_int4_tcgen05_shapes(kind, dtype):
+    """tcgen05 prefill kernel: every token-block size (MB 32/64/128/256), ragged M and N tails,
+    K = 13696 (214 k-stages), bias, and M <= 8 forced through the tensor-core path."""
+    for (m, k, n, with_bias) in [(9, 4096, 1280, False), (33, 512, 256, True), (100, 4096, 4608, True),
+                                 (128, 13696, 4096, False), (300, 4096, 1296, True), (5, 4096, 512, False),
+                                 (520, 1024, 2064, False)]:
+        a, bq, s = make_int4_case(500 + m + n, m, k, n, kind, dtype)
+        bias = orc.round_to(np.random.default_rng(n).standard_normal(n) * 0.1, dtype) if with_bias else None
+        want = c_oracle.w4a16_gemm(a, bq, s, bias, dtype)
+        got = run4(a, bq, s, dtype, bias=bias, impl=ops.IMPL_TC)
+        assert_parity(got, want, f"int4 tc {kind} {dtype} M={m} K={k} N={n}", rtol=rtol_for(dtype))
+
+
+def test_int4_tcgen05_matches_simple_bitwise_dequant():
+    """The tensor-core path feeds the reference's own rounded weights: against the bit-faithful CUDA-core
+    kernel only the fp32 summation order differs, so the outputs agree to ~1 ulp of fp16."""
+    a, bq, s = make_int4_case(901, 256, 4096, 4096, "Q")
+    y_tc = run4(a, bq, s, "float16", impl=ops.IMPL_TC)
+    y_s = run4(a, bq, s, "float16", impl=ops.IMPL_SIMPLE)
+    rms = float(np.sqrt(np.mean(y_s * y_s)))
+    assert np.abs(y_tc - y_s).max() <= 2e-3 * rms + 2e-3 * np.abs(y_s).max()
+    # deterministic
+    assert np.array_equal(y_tc, run4(a, bq, s, "float16", impl=ops.IMPL_TC))
 
 
 # ------------------------------------------------------------------ edge cases
