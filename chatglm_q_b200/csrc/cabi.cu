@@ -255,12 +255,20 @@ extern "C" int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, c
   if (impl == CGQ_IMPL_AUTO) {
     if (M <= 8 && w8_gemv_supported(a) && workspace != nullptr && workspace_bytes >= kWorkspaceBytes)
       impl = CGQ_IMPL_GEMV;
+    else if (M > 8 && w8_tc_supported(a))
+      impl = CGQ_IMPL_TC;
     else
       impl = CGQ_IMPL_SIMPLE;
   }
   switch (impl) {
     case CGQ_IMPL_SIMPLE:
       return launch_w8_simple(a);
+    case CGQ_IMPL_TC:
+      if (!w8_tc_supported(a)) {
+        set_error("%s: tcgen05 kernel needs K%%16==0, 16-byte aligned pointers, lda%%8==0", fn);
+        return CGQ_ERR_MISALIGNED;
+      }
+      return launch_w8_tc(a);
     case CGQ_IMPL_GEMV:
       if (M > 8 || !w8_gemv_supported(a)) {
         set_error("%s: GEMV kernel needs M<=8, K%%16==0, 16-byte aligned pointers, lda%%8==0", fn);

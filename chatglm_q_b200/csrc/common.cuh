@@ -93,6 +93,8 @@ int launch_w4_gemv(const GemmArgs& a, bool exact);
 int launch_w8_gemv(const GemmArgs& a);
 int launch_w4_tc(const GemmArgs& a);
 bool w4_tc_supported(const GemmArgs& a);
+int launch_w8_tc(const GemmArgs& a);
+bool w8_tc_supported(const GemmArgs& a);
 bool w4_gemv_supported(const GemmArgs& a);
 bool w8_gemv_supported(const GemmArgs& a);
 

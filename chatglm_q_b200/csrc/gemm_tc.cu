@@ -21,6 +21,10 @@
 //               tcgen05.commit releases the smem stages; owns the TMEM allocation (2 accumulators)
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 bit) -> round to T -> (+ bias, second rounding)
 //               -> C, overlapped with the next tile's MMAs through the second accumulator
+//
+// The int8 variant (chatglm_q/int8/triton_ops.py:13-84) shares the skeleton: its weight is [N, K]
+// K-contiguous, so the dequantised tile (round_T(q * scale[n]), int8/qlinear.py:38) is a K-major A
+// operand; the packed stage is [128 n x 64 k] bytes and the per-channel scales come from global memory.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -33,9 +37,10 @@ constexpr int BK = 64;           // k per pipeline stage      (4 UMMA K-steps)
 constexpr int STAGES = 4;        // TMA ring depth
 constexpr int ABUFS = 2;         // dequantised-A double buffer
 constexpr int kThreads = 320;
-constexpr int P_BYTES = (BK / 2) * TN;       // 4096: packed tile
+constexpr int P_BYTES = (BK / 2) * TN;       // 4096: packed int4 tile
 constexpr int S_BYTES = (BK / 32) * TN * 2;  // 512: scale tile
 constexpr int PS_BYTES = 5120;               // packed + scales, padded to keep B tiles 1024-aligned
+constexpr int P8_BYTES = TN * BK;            // 8192: int8 tile [128 n x 64 k]
 constexpr int A_BYTES = TN * BK * 2;         // 16384: dequantised tile
 constexpr int ATOM = 1024;                   // 8 rows x 128 B swizzle atom
 
@@ -47,6 +52,7 @@ struct Params {
   int MB;        // tokens per tile (UMMA N)
   int n_tiles, m_blocks, k_stages;
   uint32_t idesc;
+  const void* scale8;   // int8 variant: per-channel scales [N]
 };
 
 // 64-bit shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
@@ -110,16 +116,40 @@ struct Deq<__nv_bfloat16> {
   }
 };
 
+// word = 4 consecutive int8 (k..k+3) of one weight row -> round_T(q * s) pairs (k,k+1), (k+2,k+3);
+// s2 = (s, s).  int8 -> T is exact, the multiply rounds once (int8/qlinear.py:38).
 template <typename T>
+struct Deq8;
+template <>
+struct Deq8<__half> {
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t s2, uint32_t& p01, uint32_t& p23) {
+    const uint32_t x = w ^ 0x80808080u;  // q + 128 as unsigned bytes
+    p01 = h2_mul(h2_sub(__byte_perm(x, 0x64646464u, 0x4140), 0x64806480u), s2);  // (1024+128+q) - 1152
+    p23 = h2_mul(h2_sub(__byte_perm(x, 0x64646464u, 0x4342), 0x64806480u), s2);
+  }
+};
+template <>
+struct Deq8<__nv_bfloat16> {
+  __device__ static __forceinline__ uint32_t one(uint32_t x, int sel) {
+    return __float_as_uint(__uint_as_float(__byte_perm(x, 0x4B000000u, sel)) - 8388736.f);  // exact q
+  }
+  __device__ static __forceinline__ void run(uint32_t w, uint32_t s2, uint32_t& p01, uint32_t& p23) {
+    const uint32_t x = w ^ 0x80808080u;
+    p01 = bf2_mul(__byte_perm(one(x, 0x7440), one(x, 0x7441), 0x7632), s2);  // high halves = bf16(q)
+    p23 = bf2_mul(__byte_perm(one(x, 0x7442), one(x, 0x7443), 0x7632), s2);
+  }
+};
+
+template <typename T, bool kW8>
 __global__ void __launch_bounds__(kThreads, 1)
-    w4_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmS,
+    wq_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmS,
                       const __grid_constant__ CUtensorMap tmA, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
   const int MB = p.MB;
   const uint32_t b_bytes = static_cast<uint32_t>(MB) * 128u;   // [MB tokens x 64 k] 16-bit
-  const uint32_t stage_bytes = b_bytes + PS_BYTES;
+  const uint32_t stage_bytes = b_bytes + (kW8 ? P8_BYTES : PS_BYTES);
   // layout: A buffers | stages { B tile | packed | scales } | barriers | tmem ptr
   const uint32_t off_stage = ABUFS * A_BYTES;
   const uint32_t off_bar = off_stage + STAGES * stage_bytes;
@@ -139,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 8 * 32) {
     ptx::prefetch_tmap(&tmP);
-    ptx::prefetch_tmap(&tmS);
+    if (!kW8) ptx::prefetch_tmap(&tmS);
     ptx::prefetch_tmap(&tmA);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_tma[s], 1);
@@ -175,10 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int ks = 0; ks < p.k_stages; ++ks) {
           ptx::mbar_wait(&empty_tma[s], ph ^ 1);
           uint8_t* st = gen + off_stage + s * stage_bytes;
-          ptx::mbar_expect_tx(&full_tma[s], b_bytes + P_BYTES + S_BYTES);
+          ptx::mbar_expect_tx(&full_tma[s], b_bytes + (kW8 ? P8_BYTES : P_BYTES + S_BYTES));
           ptx::tma_load_2d(st, &tmA, ks * BK, mb * MB, &full_tma[s], pol_a);
-          ptx::tma_load_2d(st + b_bytes, &tmP, nt * TN, ks * (BK / 2), &full_tma[s], pol_w);
-          ptx::tma_load_2d(st + b_bytes + P_BYTES, &tmS, nt * TN, ks * (BK / 32), &full_tma[s], pol_w);
+          if (kW8) {
+            ptx::tma_load_2d(st + b_bytes, &tmP, ks * BK, nt * TN, &full_tma[s], pol_w);
+          } else {
+            ptx::tma_load_2d(st + b_bytes, &tmP, nt * TN, ks * (BK / 2), &full_tma[s], pol_w);
+            ptx::tma_load_2d(st + b_bytes + P_BYTES, &tmS, nt * TN, ks * (BK / 32), &full_tma[s], pol_w);
+          }
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -202,8 +236,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t b_addr = base + off_stage + s * stage_bytes;
 #pragma unroll
           for (int k4 = 0; k4 < BK / 16; ++k4) {
-            // A: MN-major, 64-column halves 8 KB apart (LBO), 8-k atoms 1 KB apart (SBO)
-            const uint64_t adesc = make_desc(a_addr + k4 * 2 * ATOM, (BK / 8) * ATOM, ATOM);
+            // int4 A: MN-major, 64-column halves 8 KB apart (LBO), 8-k atoms 1 KB apart (SBO)
+            // int8 A: K-major rows of 128 B like B
+            const uint64_t adesc = kW8 ? make_desc(a_addr + k4 * 32, 16, ATOM)
+                                       : make_desc(a_addr + k4 * 2 * ATOM, (BK / 8) * ATOM, ATOM);
             // B: K-major rows of 128 B, 8-row atoms 1 KB apart; K-step = 32 B inside the row
             const uint64_t bdesc = make_desc(b_addr + k4 * 32, 16, ATOM);
             ptx::umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (ks | k4) != 0 ? 1u : 0u);
@@ -232,49 +268,99 @@ __global__ void __launch_bounds__(kThreads, 1)
     // 32 packed rows x 16 chunks.  Chunk element order is (c0,c2,c1,c3,c4,c6,c5,c7): the epilogue
     // un-permutes the TMEM lanes.
     const int t = threadIdx.x - 128;
-    const int c = t & 15;          // column chunk: columns 8c .. 8c+7
-    const int r0 = t >> 4;         // 0..7
     int s = 0, ph = 0, ab = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int ks = 0; ks < p.k_stages; ++ks) {
-        ptx::mbar_wait(&full_tma[s], ph);
-        const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
-        uint32_t out[4][8];  // [row i][k parity * 4 + word]
+    if constexpr (kW8) {
+      // thread -> (16-byte chunk j = 8 consecutive k, weight rows r0 + 16 i): 128 rows x 8 chunks
+      const int j = t & 7, r0 = t >> 3;
+      const T* sc = static_cast<const T*>(p.scale8);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / p.m_blocks;
+        uint32_t s2[8];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint4 sv = ptx::lds128(st + P_BYTES + g * (TN * 2) + c * 16);
-          const uint32_t s02a = __byte_perm(sv.x, sv.y, 0x5410), s13a = __byte_perm(sv.x, sv.y, 0x7632);
-          const uint32_t s02b = __byte_perm(sv.z, sv.w, 0x5410), s13b = __byte_perm(sv.z, sv.w, 0x7632);
+        for (int i = 0; i < 8; ++i) {
+          const int n = nt * TN + r0 + 16 * i;
+          union {
+            uint32_t u;
+            T h[2];
+          } cv;
+          cv.h[0] = cv.h[1] = (n < p.N) ? sc[n] : DT<T>::from_f(0.f);
+          s2[i] = cv.u;
+        }
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          ptx::mbar_wait(&full_tma[s], ph);
+          const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
+          uint32_t out[8][4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int i = 2 * g + h;                 // packed row r0 + 8 i  (rows 0..15 = group 0)
-            const uint2 pk = ptx::lds64(st + (r0 + 8 * i) * TN + c * 8);
-            Deq<T>::run(pk.x, s02a, s13a, out[i][0], out[i][1], out[i][4], out[i][5]);
-            Deq<T>::run(pk.y, s02b, s13b, out[i][2], out[i][3], out[i][6], out[i][7]);
+          for (int i = 0; i < 8; ++i) {
+            const uint2 pk = ptx::lds64(st + (r0 + 16 * i) * BK + j * 8);
+            Deq8<T>::run(pk.x, s2[i], out[i][0], out[i][1]);
+            Deq8<T>::run(pk.y, s2[i], out[i][2], out[i][3]);
+          }
+          ptx::mbar_wait(&a_empty[ab], aph ^ 1);
+          const uint32_t a_addr = base + ab * A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            ptx::sts128(a_addr + (r >> 3) * ATOM + (r & 7) * 128 + ((j ^ (r & 7)) << 4),
+                        make_uint4(out[i][0], out[i][1], out[i][2], out[i][3]));
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+          if (++ab == ABUFS) {
+            ab = 0;
+            aph ^= 1;
           }
         }
-        ptx::mbar_wait(&a_empty[ab], aph ^ 1);
-        const uint32_t a_addr = base + ab * A_BYTES + (c >> 3) * ((BK / 8) * ATOM);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-          for (int par = 0; par < 2; ++par) {
-            const int k = 2 * (r0 + 8 * i) + par;    // k row inside the stage
-            const uint32_t addr = a_addr + (k >> 3) * ATOM + (k & 7) * 128 + (((c & 7) ^ (k & 7)) << 4);
-            ptx::sts128(addr, make_uint4(out[i][4 * par], out[i][4 * par + 1], out[i][4 * par + 2],
-                                         out[i][4 * par + 3]));
+      }
+    } else {
+      const int c = t & 15;          // column chunk: columns 8c .. 8c+7
+      const int r0 = t >> 4;         // 0..7
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          ptx::mbar_wait(&full_tma[s], ph);
+          const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
+          uint32_t out[4][8];  // [row i][k parity * 4 + word]
+  #pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint4 sv = ptx::lds128(st + P_BYTES + g * (TN * 2) + c * 16);
+            const uint32_t s02a = __byte_perm(sv.x, sv.y, 0x5410), s13a = __byte_perm(sv.x, sv.y, 0x7632);
+            const uint32_t s02b = __byte_perm(sv.z, sv.w, 0x5410), s13b = __byte_perm(sv.z, sv.w, 0x7632);
+  #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 2 * g + h;                 // packed row r0 + 8 i  (rows 0..15 = group 0)
+              const uint2 pk = ptx::lds64(st + (r0 + 8 * i) * TN + c * 8);
+              Deq<T>::run(pk.x, s02a, s13a, out[i][0], out[i][1], out[i][4], out[i][5]);
+              Deq<T>::run(pk.y, s02b, s13b, out[i][2], out[i][3], out[i][6], out[i][7]);
+            }
           }
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-        if (++ab == ABUFS) {
-          ab = 0;
-          aph ^= 1;
+          ptx::mbar_wait(&a_empty[ab], aph ^ 1);
+          const uint32_t a_addr = base + ab * A_BYTES + (c >> 3) * ((BK / 8) * ATOM);
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+  #pragma unroll
+            for (int par = 0; par < 2; ++par) {
+              const int k = 2 * (r0 + 8 * i) + par;    // k row inside the stage
+              const uint32_t addr = a_addr + (k >> 3) * ATOM + (k & 7) * 128 + (((c & 7) ^ (k & 7)) << 4);
+              ptx::sts128(addr, make_uint4(out[i][4 * par], out[i][4 * par + 1], out[i][4 * par + 2],
+                                           out[i][4 * par + 3]));
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+          if (++ab == ABUFS) {
+            ab = 0;
+            aph ^= 1;
+          }
         }
       }
     }
@@ -283,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     T* Cp = static_cast<T*>(p.C);
     const T* bias = static_cast<const T*>(p.bias);
     const int row = warp * 32 + lane;                       // TMEM lane = permuted column of the tile
-    const int col_in_tile = (row & ~3) | ((row & 1) << 1) | ((row >> 1) & 1);   // (0,2,1,3) un-permute
+    // int4: (0,2,1,3) un-permute of the dequant chunk order; int8: identity
+    const int col_in_tile = kW8 ? row : ((row & ~3) | ((row & 1) << 1) | ((row >> 1) & 1));
     int acc = 0, cph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile / p.m_blocks, mb = tile - nt * p.m_blocks;
@@ -320,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 9) ptx::tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <typename T>
+template <typename T, bool kW8>
 int launch_t(const GemmArgs& a) {
   const int MB = a.M > 128 ? 256 : a.M > 64 ? 128 : a.M > 32 ? 64 : 32;
   Params prm;
@@ -334,32 +421,44 @@ int launch_t(const GemmArgs& a) {
   prm.n_tiles = (a.N + TN - 1) / TN;
   prm.m_blocks = (a.M + MB - 1) / MB;
   prm.k_stages = (a.K + BK - 1) / BK;
+  prm.scale8 = a.scale;
   const uint32_t fmt = (DT<T>::code == CGQ_DTYPE_F16) ? 0u : 1u;
-  // c=F32 | a,b format | A MN-major | B K-major | N = MB | M = 128
-  prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) |
+  // c=F32 | a,b format | A major (int4: MN, int8: K) | B K-major | N = MB | M = 128
+  prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kW8 ? 0u : 1u) << 15) | (0u << 16) |
               (static_cast<uint32_t>(MB >> 3) << 17) | (static_cast<uint32_t>(TN >> 4) << 24);
 
   const CUtensorMapDataType dt16 = (DT<T>::code == CGQ_DTYPE_F16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                  : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmP, tmS, tmA;
-  TmapKey kp{a.Wq, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 2),
-             static_cast<uint64_t>(a.N), TN, BK / 2, CU_TENSOR_MAP_DATA_TYPE_UINT8,
-             CU_TENSOR_MAP_SWIZZLE_NONE};
-  int rc = get_tmap_2d(kp, &tmP);
-  if (rc != CGQ_OK) return rc;
-  TmapKey ks{a.scale, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 32),
-             static_cast<uint64_t>(a.N) * 2, TN, BK / 32, dt16, CU_TENSOR_MAP_SWIZZLE_NONE};
-  rc = get_tmap_2d(ks, &tmS);
-  if (rc != CGQ_OK) return rc;
+  int rc;
+  if (kW8) {
+    TmapKey kp{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N),
+               static_cast<uint64_t>(a.K), BK, TN, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+               CU_TENSOR_MAP_SWIZZLE_NONE};
+    rc = get_tmap_2d(kp, &tmP);
+    if (rc != CGQ_OK) return rc;
+    tmS = tmP;  // unused
+  } else {
+    TmapKey kp{a.Wq, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 2),
+               static_cast<uint64_t>(a.N), TN, BK / 2, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+               CU_TENSOR_MAP_SWIZZLE_NONE};
+    rc = get_tmap_2d(kp, &tmP);
+    if (rc != CGQ_OK) return rc;
+    TmapKey ks{a.scale, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 32),
+               static_cast<uint64_t>(a.N) * 2, TN, BK / 32, dt16, CU_TENSOR_MAP_SWIZZLE_NONE};
+    rc = get_tmap_2d(ks, &tmS);
+    if (rc != CGQ_OK) return rc;
+  }
   TmapKey ka{a.A, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M),
              static_cast<uint64_t>(a.lda) * 2, BK, static_cast<uint32_t>(MB), dt16,
              CU_TENSOR_MAP_SWIZZLE_128B};
   rc = get_tmap_2d(ka, &tmA);
   if (rc != CGQ_OK) return rc;
 
-  const size_t smem = 1024 + ABUFS * A_BYTES + static_cast<size_t>(STAGES) * (MB * 128 + PS_BYTES) +
+  const size_t smem = 1024 + ABUFS * A_BYTES +
+                      static_cast<size_t>(STAGES) * (MB * 128 + (kW8 ? P8_BYTES : PS_BYTES)) +
                       8 * (2 * STAGES + 2 * ABUFS + 4) + 16;
-  auto kern = w4_gemm_tc_kernel<T>;
+  auto kern = wq_gemm_tc_kernel<T, kW8>;
   static size_t configured[64] = {0};
   int dev = 0;
   CGQ_CUDA_TRY(cudaGetDevice(&dev));
@@ -382,9 +481,17 @@ bool w4_tc_supported(const GemmArgs& a) {
   return a.M >= 1 && a.K % 32 == 0 && a.N % 16 == 0 && al16(a.Wq) && al16(a.scale) && al16(a.A) &&
          a.lda % 8 == 0;
 }
+bool w8_tc_supported(const GemmArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return a.M >= 1 && a.K % 16 == 0 && al16(a.Wq) && al16(a.A) && a.lda % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.scale) & 1) == 0;
+}
 
 int launch_w4_tc(const GemmArgs& a) {
-  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a) : launch_t<__nv_bfloat16>(a);
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half, false>(a) : launch_t<__nv_bfloat16, false>(a);
+}
+int launch_w8_tc(const GemmArgs& a) {
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half, true>(a) : launch_t<__nv_bfloat16, true>(a);
 }
 
 }  // namespace cgq

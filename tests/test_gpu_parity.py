@@ -188,6 +188,18 @@ def test_int4_tcgen05_shapes(kind, dtype):
         assert_parity(got, want, f"int4 tc {kind} {dtype} M={m} K={k} N={n}", rtol=rtol_for(dtype))
 
 
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("kind", ["Q", "R"])
+def test_int8_tcgen05_shapes(kind, dtype):
+    for (m, k, n, with_bias) in [(10, 128, 256, False), (40, 4096, 1000, True), (128, 13696, 4096, False),
+                                 (300, 4096, 4608, True), (3, 4096, 512, False), (700, 1040, 2048, False)]:
+        a, q, s = make_int8_case(600 + m + n, m, k, n, kind, dtype)
+        bias = orc.round_to(np.random.default_rng(n).standard_normal(n) * 0.1, dtype) if with_bias else None
+        want = c_oracle.w8a16_gemm(a, q, s, bias, dtype)
+        got = run8(a, q, s, dtype, bias=bias, impl=ops.IMPL_TC)
+        assert_parity(got, want, f"int8 tc {kind} {dtype} M={m} K={k} N={n}", rtol=rtol_for(dtype))
+
+
 def test_int4_tcgen05_matches_simple_bitwise_dequant():
     """The tensor-core path feeds the reference's own rounded weights: against the bit-faithful CUDA-core
     kernel only the fp32 summation order differs, so the outputs agree to ~1 ulp of fp16."""
