@@ -2,13 +2,18 @@
 // Replaces _dynamic_quant_matmul_s4_kernel (chatglm_q/int4/triton_ops.py:18-87) for decode.
 //
 // HBM-bound design (B200: 148 SMs, ~6.5 TB/s measured):
-//   * persistent stream-K grid: the (column-tile, k-stage) units are cut into gridDim.x equal
-//     contiguous ranges, so every SM streams the same number of bytes whatever N is;
-//   * small CTAs (4 consumer warps + 1 producer warp, ~50 KB of shared memory at M=1), two per SM
-//     per launch, so that the CTAs of the NEXT launch fit beside them: with programmatic dependent
-//     launch the next kernel's producers fill their rings with weights (which do not depend on the
-//     previous kernel) while this kernel is still computing — the HBM stream does not stop at
-//     kernel boundaries, which is what a chain of 1.5 µs GEMVs needs;
+//   * work split = (128-column tile) x (Z contiguous k-bands); one CTA per (tile, band), the Z CTAs
+//     of a tile form a thread-block CLUSTER.  All CTAs start at the top of their band and walk down
+//     in lockstep, so at any moment the chip reads a few row bands of the [K/2, N] byte matrix that
+//     are contiguous across ALL column tiles: the access pattern DRAM likes (measured: scattered
+//     stream-K strips cap at ~4.5 TB/s with no compute at all, lockstep bands reach 5.8 TB/s);
+//   * the Z band sums of a tile are reduced through DISTRIBUTED SHARED MEMORY (st.shared::cluster
+//     into rank 0 + barrier.cluster), in rank order: deterministic, no workspace, no global
+//     round trips on the critical path of a 1.5 us layer;
+//   * small CTAs (4 consumer warps + 1 producer warp, ~45 KB of shared memory at M=1), at most two
+//     per SM per launch, so that the CTAs of the NEXT launch fit beside them: with programmatic
+//     dependent launch the next kernel's producers fill their rings with weights (which do not
+//     depend on the previous kernel) while this kernel is still computing;
 //   * one producer lane per CTA feeds an S-deep shared-memory ring with TMA: a [64 x 128] byte
 //     tile of packed weights (128-byte swizzle), the [4 x 128] scale tile, and the matching
 //     128-k slice of each activation row (cp.async.bulk), all landing on one mbarrier;
@@ -22,9 +27,7 @@
 //   * fp16 fast variant ("trick"): the masked nibble IS an fp16 subnormal q·2^-24 (q·2^-20 for
 //     the high nibble, compensated by scaling the odd-k activations by 2^-4), so no int->fp
 //     conversion is executed at all; the -8 offset becomes -8·Σ_{k∈g} a_k, obtained from one
-//     extra MMA against a constant fragment;
-//   * tiles cut by a range boundary are reduced deterministically: partial tiles go to a
-//     workspace slot, the last arriver (self-cleaning counter) sums the slots in CTA order.
+//     extra MMA against a constant fragment.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -49,10 +52,9 @@ struct Cfg {
   static constexpr int MR = kM1 ? 1 : MMAX;           // token rows staged / reduced
   static constexpr int A_BYTES = MR * A_STRIDE;
   static constexpr int RED_BYTES = CW * MR * BN * 4;
+  static constexpr int XRED_BYTES = 8 * MR * BN * 4;   // band sums of up to 8 cluster ranks (rank 0)
   static constexpr int STAGE_BYTES = W_BYTES + S_BYTES + A_BYTES;
 };
-
-static_assert(kSlotFloats == MMAX * BN, "workspace slot size");
 
 __device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
   uint32_t r;
@@ -111,19 +113,11 @@ struct Params {
   int64_t ldc;
   int M, N, K;
   int SPT;     // k-stages per column tile
-  int U;       // total units = tiles * SPT
+  int Z;       // k-bands per tile == cluster size
   int S;       // ring depth
-  int* counters;
-  float* partials;
   unsigned long long* trace;  // optional timeline (cgq_debug_trace), 8 words per CTA
 };
 
-__device__ __forceinline__ int unit_begin(int U, int P, int c) {
-  return static_cast<int>(static_cast<int64_t>(U) * c / P);
-}
-__device__ __forceinline__ int unit_owner(int U, int P, int u) {
-  return static_cast<int>((static_cast<int64_t>(u + 1) * P - 1) / U);
-}
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
   if (p.trace != nullptr && blockIdx.x < 1024) {
     unsigned long long t;
@@ -147,13 +141,14 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   const uint32_t Asm = Ssm + S * S_BYTES;
   const uint32_t off_red = S * C::STAGE_BYTES;
   float* red = reinterpret_cast<float*>(gen + off_red);
-  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES);
+  float* xred = reinterpret_cast<float*>(gen + off_red + C::RED_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES + C::XRED_BYTES);
   uint64_t* empty = full + S;
-  int* flag = reinterpret_cast<int*>(empty + S);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = gridDim.x, c = blockIdx.x;
-  const int u0 = unit_begin(p.U, P, c), u1 = unit_begin(p.U, P, c + 1);
+  const int Z = p.Z;
+  const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;   // z == rank in the cluster
+  const int u0 = p.SPT * z / Z, u1 = p.SPT * (z + 1) / Z;      // this CTA's k-stages of the tile
   const int n_units = u1 - u0;
   const T* A = static_cast<const T*>(p.A);
 
@@ -181,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       stamp(p, 1);
       const uint64_t pol = ptx::policy_evict_first();
       auto issue_w = [&](int i, int slot) {
-        const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
+        const int ks = u0 + i;
         const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
         ptx::mbar_expect_tx(&full[slot], W_BYTES + S_BYTES + p.M * kvalid * 2);
         ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, tile * BN, ks * ROWS, &full[slot], pol);
@@ -189,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
                          pol);
       };
       auto issue_a = [&](int i, int slot) {
-        const int u = u0 + i, tile = u / p.SPT, ks = u - tile * p.SPT;
+        const int ks = u0 + i;
         const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
         uint8_t* dst = gen + S * (W_BYTES + S_BYTES) + slot * C::A_BYTES;
         if (kM1) {
@@ -216,9 +211,8 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         }
       }
     }
-    return;
-  }
-
+    __syncwarp();
+  } else {
   // =========================== consumers ===========================
   ptx::pdl_wait_prior_grid();
   if (threadIdx.x == 0) stamp(p, 2);
@@ -232,7 +226,6 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 
   const bool has_tok = kM1 ? (g == 0) : (g < p.M);
   int slot = 0, phase = 0;
-  int tile = u0 / p.SPT, ks = u0 - tile * p.SPT;  // tracked incrementally (no division in the loop)
   for (int it = 0; it < n_units; ++it) {
     ptx::mbar_wait(&full[slot], phase);
     if (it == 0 && threadIdx.x == 0) stamp(p, 3);
@@ -242,9 +235,16 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 
     float grp[8][4];
     float ag[4];
-    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+#ifdef CGQ_HACK_NO_COMPUTE
+#pragma unroll
+    for (int j = 0; j < 8; ++j) grp[j][0] = grp[j][1] = grp[j][2] = grp[j][3] = 1.f;
+    ag[0] = ag[1] = 0.f;
+    for (int b = 0; b < 0; ++b) {
+#else
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
+#endif
       const int r = 8 * b + 2 * tig;
       const uint4 q = ptx::lds128(wrow + r * BN + ((g ^ (2 * tig)) << 4));
       const uint4 pp = ptx::lds128(wrow + (r + 1) * BN + ((g ^ (2 * tig + 1)) << 4));
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       if (kTrick) {
         const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x4C004C00u, 0x4C004C00u};  // 1,1 | 16,16
         if (b == 0)
-          ptx::mma_16816(ag, ones, b0, b1, z, T());
+          ptx::mma_16816(ag, ones, b0, b1, zero4, T());
         else
           ptx::mma_16816(ag, ones, b0, b1, ag, T());
       }
@@ -269,10 +269,14 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         const uint32_t x = qw[j >> 1], y = pw[j >> 1];
         const uint32_t v0 = (j & 1) ? __byte_perm(x, y, 0x6622) : __byte_perm(x, y, 0x4400);
         const uint32_t v1 = (j & 1) ? __byte_perm(x, y, 0x7733) : __byte_perm(x, y, 0x5511);
+#ifdef CGQ_HACK_HALF_ALU
+        const uint32_t a[4] = {Nib<T, kTrick>::lo(v0), v0, Nib<T, kTrick>::hi(v0), v0};
+#else
         const uint32_t a[4] = {Nib<T, kTrick>::lo(v0), Nib<T, kTrick>::lo(v1),
                                Nib<T, kTrick>::hi(v0), Nib<T, kTrick>::hi(v1)};
+#endif
         if (b == 0)
-          ptx::mma_16816(grp[j], a, b0, b1, z, T());
+          ptx::mma_16816(grp[j], a, b0, b1, zero4, T());
         else
           ptx::mma_16816(grp[j], a, b0, b1, grp[j], T());
       }
@@ -317,98 +321,68 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       phase ^= 1;
     }
 
-    // ---------------- end of a column tile (or of this CTA's range): reduce and emit
-    if (ks == p.SPT - 1 || it == n_units - 1) {
-      if (it == n_units - 1 && threadIdx.x == 0) stamp(p, 4);
-      // (1) cross-warp (k-group) reduction through shared memory
+  }
+  if (threadIdx.x == 0) stamp(p, 4);
+
+  // ---------------- band sum of this CTA: cross-warp (k-group) reduction through shared memory
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 8; ++j) {
 #pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          const int tok = kM1 ? 0 : 2 * tig + (i & 1);
-          const int col = 16 * g + 2 * j + (kM1 ? i : (i >> 1));
-          const bool ok = kM1 ? (tig == 0) : (tok < p.M);
-          if (ok) red[(warp * MR + tok) * BN + col] = tot[j][i];
-          tot[j][i] = 0.f;
-        }
+    for (int i = 0; i < NT; ++i) {
+      const int tok = kM1 ? 0 : 2 * tig + (i & 1);
+      const int col = 16 * g + 2 * j + (kM1 ? i : (i >> 1));
+      const bool ok = kM1 ? (tig == 0) : (tok < p.M);
+      if (ok) red[(warp * MR + tok) * BN + col] = tot[j][i];
+    }
+  }
+  ptx::named_bar_sync(1, CW * 32);
+  {
+    const int t = threadIdx.x;  // column within the tile
+    float v[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      v[m] = 0.f;
+      if (m < p.M) {
+#pragma unroll
+        for (int w = 0; w < CW; ++w) v[m] += red[(w * MR + m) * BN + t];
       }
-      ptx::named_bar_sync(1, CW * 32);
-      const int t = threadIdx.x;  // column within the tile
+    }
+    if (Z == 1) {
       const int n = tile * BN + t;
-      float v[MR];
-#pragma unroll
-      for (int m = 0; m < MR; ++m) {
-        v[m] = 0.f;
-        if (m < p.M) {
-#pragma unroll
-          for (int w = 0; w < CW; ++w) v[m] += red[(w * MR + m) * BN + t];
-        }
-      }
-      // (2) is the tile cut by a range boundary?
-      const int t_first = tile * p.SPT, t_last = t_first + p.SPT - 1;
-      const bool whole = (u0 <= t_first) && (u1 > t_last);
-      bool write_out = whole;
-      if (!whole) {
-        const int my_slot = c * 2 + ((tile == u0 / p.SPT) ? 0 : 1);
-        float* mine = p.partials + static_cast<size_t>(my_slot) * kSlotFloats;
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < p.M) mine[m * BN + t] = v[m];
-        ptx::named_bar_sync(1, CW * 32);  // every partial of this CTA is issued ...
-        const int c_first = unit_owner(p.U, P, t_first), c_last = unit_owner(p.U, P, t_last);
-        if (t == 0) {
-          ptx::fence_acq_rel_gpu();       // ... and made visible (cumulative) before the count
-          const int old = atomicAdd(&p.counters[tile * kCounterStride], 1);
-          const int last = (old == c_last - c_first) ? 1 : 0;
-          if (last) {
-            p.counters[tile * kCounterStride] = 0;         // self-cleaning: every contributor has arrived
-            ptx::fence_acq_rel_gpu();     // acquire side: the others' partials are visible
-          }
-          *flag = last;
-          if (it == n_units - 1) stamp(p, 6);
-        }
-        ptx::named_bar_sync(1, CW * 32);
-        write_out = (*flag != 0);
-        if (write_out) {
-          // Contributor cc > c_first starts inside this tile (its first tile -> slot 0); c_first
-          // uses slot 1 iff its range began in an earlier tile.
-          const int first_slot = (unit_begin(p.U, P, c_first) < t_first) ? 1 : 0;
-#pragma unroll
-          for (int m = 0; m < MR; ++m) v[m] = 0.f;
-          // fixed order -> deterministic sum; loads are issued in batches so that their L2
-          // latencies overlap instead of adding up (the tile has up to ~10 contributors)
-          constexpr int CH = kM1 ? 8 : 2;
-          for (int cb = c_first; cb <= c_last; cb += CH) {
-            float ld[CH][MR];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              const int cc = cb + i;
-              const int sl = cc * 2 + (cc == c_first ? first_slot : 0);
-              const float* src = p.partials + static_cast<size_t>(sl) * kSlotFloats;
-#pragma unroll
-              for (int m = 0; m < MR; ++m)
-                ld[i][m] = (cc <= c_last && m < p.M) ? ptx::ldcg_f32(src + m * BN + t) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-#pragma unroll
-              for (int m = 0; m < MR; ++m) v[m] += ld[i][m];
-          }
-          if (t == 0) stamp(p, 7);
-        }
-      }
-      if (write_out && n < p.N) {
+      if (n < p.N) {
         T* Cp = static_cast<T*>(p.C);
         const T* bias = static_cast<const T*>(p.bias);
 #pragma unroll
         for (int m = 0; m < MR; ++m)
           if (m < p.M) Cp[m * p.ldc + n] = epilogue<T>(v[m], bias, n);
       }
-      ptx::named_bar_sync(1, CW * 32);  // red[] / flag may be reused
+    } else {
+      // push the band sum into rank 0's shared memory (DSMEM); rank 0 adds them in rank order
+      const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>((z * MR) * BN + t) * 4u;
+      const uint32_t remote = ptx::mapa_rank(local, 0);
+#pragma unroll
+      for (int m = 0; m < MR; ++m)
+        if (m < p.M) ptx::st_cluster_f32(remote + m * BN * 4, v[m]);
     }
-    if (++ks == p.SPT) {
-      ks = 0;
-      ++tile;
+  }
+  }  // consumers
+  if (Z > 1) {
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    if (z == 0 && threadIdx.x < BN) {
+      const int t = threadIdx.x, n = tile * BN + t;
+      if (n < p.N) {
+        T* Cp = static_cast<T*>(p.C);
+        const T* bias = static_cast<const T*>(p.bias);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+          if (m < p.M) {
+            float acc = 0.f;
+            for (int zz = 0; zz < Z; ++zz) acc += xred[(zz * MR + m) * BN + t];
+            Cp[m * p.ldc + n] = epilogue<T>(acc, bias, n);
+          }
+        }
+      }
     }
   }
   if (threadIdx.x == 0) stamp(p, 5);
@@ -427,8 +401,8 @@ template <typename T, bool kTrick, bool kM1>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
                 int grid, int stages, bool pdl) {
   using C = Cfg<kM1>;
-  const size_t smem =
-      1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES + 16 * stages + 16;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
+                      C::XRED_BYTES + 16 * stages + 16;
   auto kern = w4_gemv_kernel<T, kTrick, kM1>;
   static size_t configured[64] = {0};
   int dev = 0;
@@ -443,11 +417,22 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = a.stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (prm.Z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(prm.Z);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmW, tmS, prm));
   return CGQ_OK;
 }
@@ -457,13 +442,22 @@ int launch_t(const GemmArgs& a, bool exact) {
   const int G = a.K / 32;
   const int SPT = (G + CW - 1) / CW;
   const int tiles = (a.N + BN - 1) / BN;
-  const int U = tiles * SPT;
-  static const int stages = env_int("CGQ_GEMV_STAGES", 4, 2, 16);
-  static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 2, 1, 4);
+  static const int stages_env = env_int("CGQ_GEMV_STAGES", 0, 0, 16);
+  static const int z_env = env_int("CGQ_GEMV_Z", 0, 0, 8);
   static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
-  int grid = sm_count() * cps;
-  if (grid > kMaxCtas) grid = kMaxCtas;
-  if (grid > U) grid = U;
+  // k-bands per tile: fill the CTA slots of the SMs in one wave, powers of two up to the portable
+  // cluster size, never more bands than k-stages
+  static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 4, 1, 4);
+  const int slots = cps * sm_count();
+  int Z = 1;
+  while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
+  if (z_env > 0) Z = z_env;
+  if (Z > SPT) Z = 1;
+  const int grid = tiles * Z;
+  // fewer CTAs than slots -> deeper rings keep the same number of bytes in flight
+  int stages = stages_env > 0 ? stages_env : (grid * 4 <= slots * 3 ? 6 : 4);
+  const int per_cta = (SPT + Z - 1) / Z;
+  if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
 
   CUtensorMap tmW, tmS;
   TmapKey kw{a.Wq, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 2),
@@ -489,10 +483,8 @@ int launch_t(const GemmArgs& a, bool exact) {
   prm.N = a.N;
   prm.K = a.K;
   prm.SPT = SPT;
-  prm.U = U;
+  prm.Z = Z;
   prm.S = stages;
-  prm.counters = static_cast<int*>(a.workspace);
-  prm.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kCounterBytes);
   prm.trace = static_cast<unsigned long long*>(take_trace_buffer());
 
   constexpr bool kIsHalf = (DT<T>::code == CGQ_DTYPE_F16);
@@ -509,9 +501,8 @@ int launch_t(const GemmArgs& a, bool exact) {
 
 bool w4_gemv_supported(const GemmArgs& a) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const int tiles = (a.N + BN - 1) / BN;
   return a.M >= 1 && a.M <= MMAX && a.K % 32 == 0 && a.N % 16 == 0 && al16(a.Wq) &&
-         al16(a.scale) && al16(a.A) && a.lda % 8 == 0 && tiles <= kMaxTiles;
+         al16(a.scale) && al16(a.A) && a.lda % 8 == 0 && true;
 }
 
 int launch_w4_gemv(const GemmArgs& a, bool exact) {
