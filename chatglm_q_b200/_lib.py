@@ -30,7 +30,7 @@ SYMBOLS = {
                                  c_void_p]),
 }
 
-IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC = 0, 1, 2, 3, 4
+IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC, IMPL_GEMV_UMMA = 0, 1, 2, 3, 4, 5
 
 _lib = None
 

@@ -211,6 +211,20 @@ extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, 
   switch (impl) {
     case CGQ_IMPL_SIMPLE:
       return launch_w4_simple(a);
+    case CGQ_IMPL_GEMV_UMMA: {
+      if (M != 1 || !w4_gemv_supported(a)) {
+        set_error("%s: tcgen05 decode kernel needs M==1, N%%16==0, 16-byte aligned pointers", fn);
+        return CGQ_ERR_MISALIGNED;
+      }
+      bool taken = false;
+      rc = launch_w4_gemv_umma(a, &taken);
+      if (rc != CGQ_OK) return rc;
+      if (!taken) {
+        set_error("%s: shape too large for the tcgen05 decode kernel's shared-memory rings", fn);
+        return CGQ_ERR_BAD_SHAPE;
+      }
+      return CGQ_OK;
+    }
     case CGQ_IMPL_TC:
       if (!w4_tc_supported(a)) {
         set_error("%s: tcgen05 kernel needs K%%32==0, N%%16==0, 16-byte aligned pointers, lda%%8==0", fn);

@@ -506,6 +506,12 @@ bool w4_gemv_supported(const GemmArgs& a) {
 }
 
 int launch_w4_gemv(const GemmArgs& a, bool exact) {
+  static const bool umma_default = env_int("CGQ_GEMV_UMMA", 0, 0, 1) != 0;
+  if (umma_default && !exact && a.M == 1) {   // opt-in: integer tcgen05 decode kernel (gemv_w4_umma.cu)
+    bool taken = false;
+    const int rc = launch_w4_gemv_umma(a, &taken);
+    if (rc != CGQ_OK || taken) return rc;
+  }
   return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, exact) : launch_t<__nv_bfloat16>(a, exact);
 }
 

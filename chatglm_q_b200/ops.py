@@ -12,7 +12,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_SIMPLE, IMPL_TC  # noqa: F401
+from ._lib import IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_GEMV_UMMA, IMPL_SIMPLE, IMPL_TC  # noqa: F401
 
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 _workspaces: dict[tuple[int, int], Tensor] = {}

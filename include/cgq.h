@@ -40,9 +40,10 @@ extern "C" {
 /* Kernel selection for the *_ex entry points (tests / bench / profiling only). */
 #define CGQ_IMPL_AUTO 0             /* what cgq_w4a16_gemm / cgq_w8a16_gemm pick */
 #define CGQ_IMPL_SIMPLE 1           /* one-thread-per-column CUDA-core kernel, bit-faithful dequant */
-#define CGQ_IMPL_GEMV 2             /* TMA-fed stream-K mma kernel, M <= 8 (decode) */
+#define CGQ_IMPL_GEMV 2             /* TMA-fed cluster mma.sync kernel, M <= 8 (decode) */
 #define CGQ_IMPL_GEMV_EXACT 3       /* same, dequant via exact (q-8) fp16 subtraction instead of subnormal trick */
 #define CGQ_IMPL_TC 4               /* tcgen05 tensor-core GEMM (prefill) */
+#define CGQ_IMPL_GEMV_UMMA 5        /* M == 1 decode on integer tcgen05 (int8 digits of the activation), opt-in */
 
 /* Library / ABI version: (major << 16) | minor. */
 int cgq_version(void);

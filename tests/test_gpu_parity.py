@@ -21,7 +21,7 @@ from chatglm_q_b200 import ops  # noqa: E402
 
 DEV = "cuda"
 IMPLS4 = {"auto": ops.IMPL_AUTO, "simple": ops.IMPL_SIMPLE, "gemv": ops.IMPL_GEMV,
-          "gemv_exact": ops.IMPL_GEMV_EXACT, "tc": ops.IMPL_TC}
+          "gemv_exact": ops.IMPL_GEMV_EXACT, "tc": ops.IMPL_TC, "umma": ops.IMPL_GEMV_UMMA}
 
 
 def u8(x):
@@ -129,6 +129,31 @@ def test_int4_decode_shapes(impl, kind, m):
         want = c_oracle.w4a16_gemm(a, bq, s, None, "float16")
         got = run4(a, bq, s, "float16", impl=IMPLS4[impl])
         assert_parity(got, want, f"int4 {impl} {kind} M={m} K={k} N={n}")
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("kind", ["Q", "R"])
+def test_int4_decode_umma(kind, dtype):
+    """Integer-tcgen05 batch-1 decode kernel (activation as three int8 digits, exact int32 group sums)."""
+    for (k, n, with_bias) in [(4096, 4608, True), (4096, 4096, False), (13696, 4096, False), (512, 256, False),
+                              (4096, 27392, False), (4096, 1296, True)]:
+        a, bq, s = make_int4_case(77 + n + k, 1, k, n, kind, dtype)
+        bias = orc.round_to(np.random.default_rng(n).standard_normal(n) * 0.1, dtype) if with_bias else None
+        want = c_oracle.w4a16_gemm(a, bq, s, bias, dtype)
+        got = run4(a, bq, s, dtype, bias=bias, impl=ops.IMPL_GEMV_UMMA)
+        assert_parity(got, want, f"int4 umma {kind} {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+    # wide dynamic range inside a group (digits keep 21 bits below the group maximum) and a one-hot row
+    k, n = 4096, 512
+    a, bq, s = make_int4_case(5, 1, k, n, "Q", dtype)
+    a[0, ::7] *= 1e-3
+    a[0, 5::64] *= 300.0
+    a = orc.round_to(a, dtype)
+    assert_parity(run4(a, bq, s, dtype, impl=ops.IMPL_GEMV_UMMA), c_oracle.w4a16_gemm(a, bq, s, None, dtype),
+                  f"int4 umma dynamic range {dtype}", rtol=rtol_for(dtype))
+    e = np.zeros((1, k), dtype=np.float32)
+    e[0, 1234] = 1.0
+    got = run4(e, bq, s, dtype, impl=ops.IMPL_GEMV_UMMA)
+    assert np.array_equal(got, orc.unpack_int4(bq, s, dtype)[1234][None, :])
 
 
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
