@@ -22,16 +22,22 @@
 //         acc_n += s[g,n] · 2^(e-19) · Σ_k (q_k - 8)·T_k
 //     which is Σ_g s_g Σ_k a_k (q_k-8) — the value the mma.sync kernel computes — to fp32 rounding.
 //
-// STATUS (B200, round 1): bit-for-bit parity-tested, but NOT the default decode kernel: the int8 A
-// operand goes through shared memory (2x the packed bytes written, then read again by the tensor
-// core: ~55 KB of shared-memory traffic per 9 KB stage), which caps it at the same ~4.8 TB/s as the
-// mma.sync kernel.  Select with CGQ_IMPL_GEMV_UMMA / env CGQ_GEMV_UMMA=1.  The next step is to feed A
-// through TMEM (ldmatrix.trans.b8 -> mask -> tcgen05.st.16x256b), which removes that traffic.
+// The int8 A operand never touches shared memory: `ldmatrix.m16n16.trans.b8` hands a thread four
+// consecutive packed rows of one weight column, two masks turn that register into the column's
+// (even-k, odd-k) int8 words, and `tcgen05.st.16x256b` — whose register layout is the same
+// (row = lane/4, column pair = lane%4) fragment — stores them as the column's TMEM row.  The MMA reads
+// A from TMEM, B (the digits, 2 KB per stage) from shared memory; the B k-order is permuted to match.
+// Shared-memory traffic per 9 KB stage: TMA write + one ldmatrix read + ~3 KB of scales / digits.
 //
-// Warp roles (384 threads): warps 0-3 epilogue (TMEM lane quarters), 4-7 unpack (one group of
-// every stage each), 8 TMA producer, 9 MMA issuer + TMEM allocator, 10-11 activation digits.
-// All hand-offs are per 128-k stage (4 groups): TMA ring -> {unpack, digits} -> 4 MMAs + commit ->
-// epilogue, over a ring of NS stage-slots (int8 A 16 KB + B 2 KB + 64 TMEM columns each).
+// STATUS (B200, round 1): parity-tested (tests/test_gpu_parity.py::test_int4_decode_umma), 1 028 us per
+// ChatGLM2-6B token against 1 012 us for the mma.sync kernel (gemv_w4.cu), so it stays opt-in
+// (CGQ_IMPL_GEMV_UMMA / env CGQ_GEMV_UMMA=1) until the stage hand-off latency is tuned.
+//
+// Warp roles (384 threads): warps 0-3 epilogue (TMEM lane quarters), 4-7 unpack (32 weight columns ==
+// one TMEM lane quarter each, all four groups of a stage), 8 TMA producer, 9 MMA issuer + TMEM
+// allocator, 10-11 activation digits.  All hand-offs are per 128-k stage (4 groups): TMA ring ->
+// {unpack, digits} -> 4 MMAs + commit -> epilogue, over a ring of NS stage-slots (32 TMEM columns of
+// A + 32 of D + 2 KB digits + 1 KB scales each).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -48,10 +54,12 @@ constexpr int KSTAGE = 32 * GPS;   // k per stage
 constexpr int W_BYTES = ROWS * BN;          // 8192
 constexpr int S_BYTES = GPS * BN * 2;       // 1024
 constexpr int STAGE_BYTES = W_BYTES + S_BYTES;
-constexpr int A_SLOT = 32 * BN;             // 4096: int8 [32 k x 128 n]
 constexpr int NU = 16;                      // UMMA N (3 digit columns used)
 constexpr int B_SLOT = NU * 32;             // 512: int8 [16 n x 32 k], K-major, no swizzle
-constexpr int A_STAGE = GPS * A_SLOT;           // 16384
+constexpr int ACOLS = 8;                    // TMEM columns of one group's A: 32 int8 per lane
+constexpr int DCOLS = 4;                    // TMEM column stride of one group's D (3 digit sums used;
+                                            // the 16-wide MMA outputs overlap, later groups only clobber unused columns)
+constexpr int SLOT_COLS = 32;               // per stage-slot: 32 columns of D, 32 of A
 constexpr int B_STAGE = GPS * B_SLOT;           // 2048
 constexpr int GI_STAGE = GPS * 8;               // (float I, int 8*ΣT) per group
 constexpr int SC_STAGE = GPS * BN * 2;          // 1024: the stage's group scales, copied out of the TMA ring
@@ -94,10 +102,28 @@ __device__ __forceinline__ void umma_i8_ss(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t (&r)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+// D[tmem] = A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 0, 0;\n\t"   // never accumulate: one group per MMA
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+// 16 lanes x 256 bit: thread (g = lane/4, t = lane%4) -> r0,r1 = (lane g, columns 2t, 2t+1), r2,r3 = lane g+8
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_trans_b8(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr));
+               : "r"(addr));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -116,10 +142,9 @@ __global__ void __launch_bounds__(kThreads, 2)
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
   const int S = p.S, NS = p.NA;
-  // layout: A stage-slots (1024-aligned) | TMA stages {packed | scales} | B stage-slots | group info |
-  //         xred | barriers | tmem ptr
-  const uint32_t Asl = base;
-  const uint32_t Wsm = Asl + NS * A_STAGE;
+  // layout: TMA stages {packed (1024-aligned, 128 B swizzle) | scales} | B stage-slots | group info |
+  //         scales | xred | barriers | tmem ptr
+  const uint32_t Wsm = base;
   const uint32_t Bsl = Wsm + S * STAGE_BYTES;
   const uint32_t Gi = Bsl + NS * B_STAGE;                 // [NS][GPS] x (float I, int G8)
   const uint32_t Ssl = Gi + NS * GI_STAGE;                // [NS][GPS][128] scales
@@ -128,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + off_x + p.xred_bytes);
   uint64_t* full_tma = bars;               // [S]   TMA landed
   uint64_t* empty_tma = full_tma + S;      // [S]   4 unpack warps have the stage in registers / copied
-  uint64_t* ab_full = empty_tma + S;       // [NS]  int8 A + scales (4 unpack warps) and digits (1 warp) written
+  uint64_t* ab_full = empty_tma + S;       // [NS]  int8 A in TMEM + scales (4 unpack warps) and digits (1 warp) written
   uint64_t* mma_done = ab_full + NS;       // [NS]  tcgen05.commit: D ready
   uint64_t* d_empty = mma_done + NS;       // [NS]  4 epilogue warps have read D / scales / group info: slot free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + NS);
@@ -138,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;
   const int u0 = p.SPT * z / Z, u1 = p.SPT * (z + 1) / Z;
   const int n_units = u1 - u0;
-  const uint32_t need_cols = static_cast<uint32_t>(NS * GPS * NU);
+  const uint32_t need_cols = static_cast<uint32_t>(NS * 2 * SLOT_COLS);
   const uint32_t tmem_cols = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u
                              : need_cols <= 256 ? 256u : 512u;
 
@@ -251,10 +276,15 @@ __global__ void __launch_bounds__(kThreads, 2)
         tsum += __shfl_xor_sync(0xffffffffu, tsum, 4);
         const int ss = st % NS, sph = (st / NS) & 1;
         ptx::mbar_wait(&d_empty[ss], sph ^ 1);    // previous user of the slot has been multiplied and read
-        // B[n = digit][k = 4L..4L+3]: core matrix (8 n x 16 B), k chunk (4L / 16) is 128 B further
-        const uint32_t dst = Bsl + ss * B_STAGE + grp * B_SLOT + (L >> 2) * 128 + (L & 3) * 4;
+        // B[n = digit][kk]: core matrix (8 n x 16 B), kk chunk (kk / 16) is 128 B further.  The MMA k
+        // order follows the TMEM A words: kk = 8 (k/8) + j for the even k = 8 (k/8) + 2j, kk + 4 for the odd
+        const int kk0 = 8 * (L >> 1) + 2 * (L & 1);
+        const uint32_t dst = Bsl + ss * B_STAGE + grp * B_SLOT + (kk0 >> 4) * 128 + (kk0 & 15);
 #pragma unroll
-        for (int t = 0; t < 3; ++t) sts32(dst + t * 16, dig[t]);
+        for (int t = 0; t < 3; ++t) {
+          sts16(dst + t * 16, __byte_perm(dig[t], 0, 0x4420));       // (k0, k2)
+          sts16(dst + t * 16 + 4, __byte_perm(dig[t], 0, 0x4431));   // (k1, k3)
+        }
         if (L == 0) {
           sts32(Gi + ss * GI_STAGE + grp * 8, __float_as_uint(I));
           sts32(Gi + ss * GI_STAGE + grp * 8 + 4, static_cast<uint32_t>(8 * tsum));
@@ -268,16 +298,16 @@ __global__ void __launch_bounds__(kThreads, 2)
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // the slot is known to be free (D read, A/B consumed) once its producers have filled it again
-      const uint64_t adesc0 = desc_sw128(Asl, 16, 1024);    // A: int8 MN-major, 8-k atoms 1 KB apart
       const uint64_t bdesc0 = desc_noswz(Bsl, 128, 256);    // B: int8 K-major core matrices, k chunks 128 B, n groups 256 B
+      const uint32_t a_tmem0 = tmem_base + static_cast<uint32_t>(NS * SLOT_COLS);
       int ss = 0, ph = 0;
       for (int st = 0; st < n_units; ++st) {
         ptx::mbar_wait(&ab_full[ss], ph);
         ptx::tc_fence_after();
 #pragma unroll
         for (int g = 0; g < GPS; ++g)
-          umma_i8_ss(tmem_base + static_cast<uint32_t>((ss * GPS + g) * NU),
-                     adesc0 + static_cast<uint64_t>((ss * A_STAGE + g * A_SLOT) >> 4),
+          umma_i8_ts(tmem_base + static_cast<uint32_t>(ss * SLOT_COLS + g * DCOLS),
+                     a_tmem0 + static_cast<uint32_t>(ss * SLOT_COLS + g * ACOLS),
                      bdesc0 + static_cast<uint64_t>((ss * B_STAGE + g * B_SLOT) >> 4), p.idesc);
         ptx::umma_commit(&mma_done[ss]);
         if (++ss == NS) {
@@ -287,35 +317,39 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
   } else if (warp >= 4) {
-    // =========================== unpack warps: group (warp - 4) of every stage ===========================
-    const int u = warp - 4;
+    // =========================== unpack warps: 32 weight columns (one TMEM lane quarter) each ===========================
+    const int q = warp - 4;
+    const int g8 = lane >> 2;      // fragment row (weight column within a 16-column block)
+    (void)g8;
     int s = 0, ph = 0, ss = 0, sph = 0;
-    const int chunk = lane & 7;
+    // ldmatrix row address: packed row (16 g + (lane & 15)) of the stage, 16-byte chunk 2q + (lane >> 4),
+    // 128-byte swizzle (chunk ^= row & 7; 16 g does not change row & 7)
+    const uint32_t ld_row = (lane & 15) * BN + (((2 * q + (lane >> 4)) ^ (lane & 7)) << 4);
+    const uint32_t a_lane = static_cast<uint32_t>(32 * q) << 16;
     for (int st = 0; st < n_units; ++st) {
       ptx::mbar_wait(&full_tma[s], ph);
-      const uint32_t src = Wsm + s * STAGE_BYTES + (16 * u) * BN;
-      uint4 q[4];
+      const uint32_t src = Wsm + s * STAGE_BYTES + ld_row;
+      uint32_t r[GPS][4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) q[t] = ptx::lds128(src + (t * 32 + lane) * 16);   // row (4t + lane/8), chunk lane%8
+      for (int g = 0; g < GPS; ++g) ldsm_x2_trans_b8(src + g * 16 * BN, r[g]);
       uint4 sc = make_uint4(0, 0, 0, 0);
-      if (lane < 16) sc = ptx::lds128(Wsm + s * STAGE_BYTES + W_BYTES + u * (BN * 2) + lane * 16);
+      if (lane < 16) sc = ptx::lds128(Wsm + s * STAGE_BYTES + W_BYTES + q * (BN * 2) + lane * 16);
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty_tma[s]);   // packed bytes and scales are in registers
       ptx::mbar_wait(&d_empty[ss], sph ^ 1);             // previous user of the slot has been multiplied and read
-      if (lane < 16) ptx::sts128(Ssl + ss * SC_STAGE + u * (BN * 2) + lane * 16, sc);
-      const uint32_t dstb = Asl + ss * A_STAGE + u * A_SLOT;
+      ptx::tc_fence_after();
+      if (lane < 16) ptx::sts128(Ssl + ss * SC_STAGE + q * (BN * 2) + lane * 16, sc);
+      const uint32_t a_addr = tmem_base + a_lane + static_cast<uint32_t>(NS * SLOT_COLS + ss * SLOT_COLS);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int row = 4 * t + (lane >> 3);             // packed row in the group: k = 2 row, 2 row + 1
-        const int k0 = 2 * row, k1 = k0 + 1;
-        const uint4 lo = make_uint4(q[t].x & 0x0F0F0F0Fu, q[t].y & 0x0F0F0F0Fu, q[t].z & 0x0F0F0F0Fu,
-                                    q[t].w & 0x0F0F0F0Fu);
-        const uint4 hi = make_uint4((q[t].x >> 4) & 0x0F0F0F0Fu, (q[t].y >> 4) & 0x0F0F0F0Fu,
-                                    (q[t].z >> 4) & 0x0F0F0F0Fu, (q[t].w >> 4) & 0x0F0F0F0Fu);
-        ptx::sts128(dstb + (k0 >> 3) * 1024 + (k0 & 7) * 128 + ((chunk ^ (k0 & 7)) << 4), lo);
-        ptx::sts128(dstb + (k1 >> 3) * 1024 + (k1 & 7) * 128 + ((chunk ^ (k1 & 7)) << 4), hi);
+      for (int g = 0; g < GPS; ++g) {
+        // r[g][0], r[g][1]: columns (16-block 0) g8, g8 + 8; r[g][2], r[g][3]: 16-block 1; 4 packed rows each
+        tmem_st_16x256b(a_addr + g * ACOLS, r[g][0] & 0x0F0F0F0Fu, (r[g][0] >> 4) & 0x0F0F0F0Fu,
+                        r[g][1] & 0x0F0F0F0Fu, (r[g][1] >> 4) & 0x0F0F0F0Fu);
+        tmem_st_16x256b(a_addr + (16u << 16) + g * ACOLS, r[g][2] & 0x0F0F0F0Fu, (r[g][2] >> 4) & 0x0F0F0F0Fu,
+                        r[g][3] & 0x0F0F0F0Fu, (r[g][3] >> 4) & 0x0F0F0F0Fu);
       }
-      ptx::fence_proxy_async_smem();
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ab_full[ss]);
       if (++s == S) {
@@ -336,10 +370,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       ptx::mbar_wait(&mma_done[ss], sph);
       if (st == 0 && threadIdx.x == 0) stamp(p, 3);
       ptx::tc_fence_after();
-      uint32_t d[GPS][4];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(ss * GPS * NU);
-#pragma unroll
-      for (int g = 0; g < GPS; ++g) tmem_ld_32x32b_x4(taddr + g * NU, d[g]);
+      uint32_t d[16];   // d[4 g + digit]
+      ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(ss * SLOT_COLS), d);
       uint32_t sraw[GPS];
 #pragma unroll
       for (int g = 0; g < GPS; ++g) sraw[g] = lds16(Ssl + ss * SC_STAGE + g * (BN * 2) + col * 2);
@@ -353,8 +385,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       for (int g = 0; g < GPS; ++g) {
         const float I = __uint_as_float(giw[2 * g]);
         const int G8 = static_cast<int>(giw[2 * g + 1]);
-        const int uu = (static_cast<int>(d[g][0]) * 128 + static_cast<int>(d[g][1])) * 128 +
-                       static_cast<int>(d[g][2]) - G8;
+        const int uu = (static_cast<int>(d[4 * g]) * 128 + static_cast<int>(d[4 * g + 1])) * 128 +
+                       static_cast<int>(d[4 * g + 2]) - G8;
         union {
           uint16_t u;
           T h;
@@ -409,10 +441,10 @@ int launch_t(const GemmArgs& a, bool* taken) {
   const int G = a.K / 32;
   const int SPT = (G + GPS - 1) / GPS;
   const int tiles = (a.N + BN - 1) / BN;
-  static const int stages_env = env_int("CGQ_UMMA_STAGES", 5, 2, 12);
-  static const int na_env = env_int("CGQ_UMMA_SLOTS", 3, 2, 8);
+  static const int stages_env = env_int("CGQ_UMMA_STAGES", 5, 2, 16);
+  static const int na_env = env_int("CGQ_UMMA_SLOTS", 2, 2, 8);
   static const int z_env = env_int("CGQ_GEMV_Z", 0, 0, 8);
-  static const int cps = env_int("CGQ_UMMA_CTAS_PER_SM", 2, 1, 4);
+  static const int cps = env_int("CGQ_UMMA_CTAS_PER_SM", 4, 1, 4);
   static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
   const int slots = cps * sm_count();
   int Z = 1;
@@ -425,7 +457,7 @@ int launch_t(const GemmArgs& a, bool* taken) {
   if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
   const int NA = na_env;
   const int xred_bytes = Z > 1 ? XRED_BYTES : 0;
-  const size_t smem = 1024 + static_cast<size_t>(NA) * (A_STAGE + B_STAGE + GI_STAGE + SC_STAGE) +
+  const size_t smem = 1024 + static_cast<size_t>(NA) * (B_STAGE + GI_STAGE + SC_STAGE) +
                       static_cast<size_t>(stages) * STAGE_BYTES + xred_bytes + 8 * (2 * stages + 4 * NA) + 16;
   if (smem > 113 * 1024 + 512) {
     *taken = false;
@@ -436,7 +468,7 @@ int launch_t(const GemmArgs& a, bool* taken) {
   CUtensorMap tmW, tmS;
   TmapKey kw{a.Wq, static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K / 2),
              static_cast<uint64_t>(a.N), BN, ROWS, CU_TENSOR_MAP_DATA_TYPE_UINT8,
-             CU_TENSOR_MAP_SWIZZLE_NONE};
+             CU_TENSOR_MAP_SWIZZLE_128B};
   int rc = get_tmap_2d(kw, &tmW);
   if (rc != CGQ_OK) return rc;
   TmapKey ks{a.scale, static_cast<uint64_t>(a.N), static_cast<uint64_t>(G),
@@ -459,8 +491,8 @@ int launch_t(const GemmArgs& a, bool* taken) {
   prm.NA = NA;
   prm.max_units = 0;   // the digit warp reads the activations from global memory (L2-resident)
   prm.xred_bytes = xred_bytes;
-  // c = S32 | a = u8 | b = s8 | A MN-major | B K-major | N = 16 | M = 128
-  prm.idesc = (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
+  // c = S32 | a = u8 | b = s8 | A from TMEM (K along the columns) | B K-major | N = 16 | M = 128
+  prm.idesc = (2u << 4) | (0u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
               (static_cast<uint32_t>(NU >> 3) << 17) | (static_cast<uint32_t>(BN >> 4) << 24);
   prm.trace = static_cast<unsigned long long*>(take_trace_buffer());
 
