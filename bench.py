@@ -182,35 +182,48 @@ class TokenStep:
 
 
 # ----------------------------------------------------------------------------- microbench (configs[1])
-def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392), k=4096, iters=20):
+def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392), k=4096, iters=10):
+    """BASELINE.json configs[1]: (seq x 4096) x (4096 x N) int4g32 dequant-matmul.  Per shape a CUDA graph
+    of one launch per weight copy (>= 400 MB of distinct weights per rotation, 3x the 126 MB L2) is
+    replayed `iters` times between CUDA events: per-launch device time without Python launch overhead."""
     from chatglm_q_b200 import ops
 
     out = []
     gen = torch.Generator(device=device).manual_seed(7)
+    stream = torch.cuda.Stream(device=device)
     for n in ns:
-        # >= 160 MB of distinct weights per rotation so that re-use never comes from the 126 MB L2
         per = k * n // 2 + (k // 32) * n * 2
-        copies = max(2, -(-160_000_000 // per))
+        copies = max(2, -(-400_000_000 // per))
         ws = [make_w4(torch, k, n, False, device, gen) for _ in range(copies)]
         for m in seqs:
+            use = copies if m <= 8 else min(copies, 4)   # M > 8 is tensor-bound: L2 residency is irrelevant
             a = torch.randn((m, k), device=device, generator=gen).half()
-            for i in range(3):
-                ops.dynamic_quant_matmul_s4(a, ws[i % copies][0], ws[i % copies][1])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = iters if m <= 128 else max(4, iters // 4)
-            e0.record()
-            for i in range(reps):
-                ops.dynamic_quant_matmul_s4(a, ws[i % copies][0], ws[i % copies][1])
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / reps
+            with torch.cuda.stream(stream), torch.no_grad():
+                for i in range(use):
+                    ops.dynamic_quant_matmul_s4(a, ws[i][0], ws[i][1])
+                stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for i in range(use):
+                        ops.dynamic_quant_matmul_s4(a, ws[i][0], ws[i][1])
+                for _ in range(3):
+                    g.replay()
+                stream.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(iters):
+                    g.replay()
+                e1.record(stream)
+                stream.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (iters * use)
             by, fl = w4_bytes(m, k, n, False), 2.0 * m * n * k
             out.append({"M": m, "K": k, "N": n, "us": round(us, 2),
                         "GBps": round(by / us / 1e3, 1), "TFLOPs": round(fl / us / 1e6, 2),
                         "hbm_frac": round(by / us / 1e3 / peaks["hbm_gbs"], 3),
-                        "tensor_frac": round(fl / us / 1e6 / peaks["bf16_tflops"], 4)})
-            del a
+                        "tensor_frac": round(fl / us / 1e6 / peaks["bf16_tflops"], 4),
+                        "kernel": "w4_gemv_kernel (mma.sync, TMA ring, cluster DSMEM reduce)" if m <= 8
+                                  else "wq_gemm_tc_kernel (tcgen05 + TMEM)"})
+            del a, g
         del ws
         torch.cuda.empty_cache()
     return out
@@ -271,52 +284,64 @@ def build_ref_int4_model(torch, device, seed=0):
 
 
 def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
-    """Reference ChatGLMDecoder.generate, unmodified, with this repo's kernels installed."""
+    """Reference ChatGLMDecoder.generate, unmodified, with this repo's kernels installed behind its QLinear
+    modules.  Headline `value`: the model object wrapped in chatglm_q_b200.GraphDecodeModel (one CUDA-graph
+    replay per token, same decoder, same model code); `eager` is the plain unwrapped model."""
     if import_reference() is None:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "baseline/_ref missing: reference decoder not importable"}
     from chatglm_q.decoder import ChatGLMDecoder
+    from chatglm_q_b200.graph_decode import GraphDecodeModel
     from chatglm_q_b200.install import install
+    import chatglm_q.decoder as decmod
 
     install("chatglm_q")
     cfg, model = build_ref_int4_model(torch, device)
-    dec = ChatGLMDecoder(cfg, model, StubTokenizer(prompt_len), device=device, time_log=False)
-    times = []
     real_perf = time.perf_counter
-    # the reference times each step itself (decoder.py:80-87) but only prints the figure; record the
-    # same intervals by wrapping the clock it reads
-    import chatglm_q.decoder as decmod
 
-    class _Clock:
-        @staticmethod
-        def perf_counter():
-            t = real_perf()
-            times.append(t)
-            return t
+    def run(decoder):
+        """the reference times each step itself (decoder.py:80-87) but only prints the figure; record the
+        same intervals by wrapping the clock it reads"""
+        times = []
 
-        def __getattr__(self, k):
-            return getattr(time, k)
+        class _Clock:
+            @staticmethod
+            def perf_counter():
+                t = real_perf()
+                times.append(t)
+                return t
 
-    torch.manual_seed(0)
-    for _ in dec.generate("warm-up", max_generated_tokens=8):   # allocator / tensor-map / cuBLAS warm-up
-        pass
-    torch.cuda.synchronize()
-    decmod.time = _Clock()
-    try:
-        for _ in dec.generate("bench", max_generated_tokens=gen_tokens):
+            def __getattr__(self, k):
+                return getattr(time, k)
+
+        torch.manual_seed(0)
+        for _ in decoder.generate("warm-up", max_generated_tokens=8):   # allocator / tensor maps / graph capture
             pass
-    finally:
-        decmod.time = time
-    steps = [b - a for a, b in zip(times[0::2], times[1::2])]
-    rest = steps[1:]
-    del dec, model
+        torch.cuda.synchronize()
+        decmod.time = _Clock()
+        try:
+            for _ in decoder.generate("bench", max_generated_tokens=gen_tokens):
+                pass
+        finally:
+            decmod.time = time
+        steps = [b - a for a, b in zip(times[0::2], times[1::2])]
+        rest = steps[1:]
+        return round(len(rest) / sum(rest), 2), round(steps[0], 4), len(steps)
+
+    tok = StubTokenizer(prompt_len)
+    eager, eager_prefill, _ = run(ChatGLMDecoder(cfg, model, tok, device=device, time_log=False))
+    graphed, prefill_s, n_tok = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
+                                                   tok, device=device, time_log=False))
+    del model
     torch.cuda.empty_cache()
-    return {"value": round(len(rest) / sum(rest), 2), "unit": UNIT,
-            "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
-            "how": f"reference ChatGLMDecoder.generate (unmodified) + chatglm_q_b200.install(); prompt {prompt_len} tok, "
-                   f"{len(steps)} tok generated, 'gen' tok/s = tokens after the first / their summed wall time "
-                   f"(each step: H2D token id, model forward, top-p sampling, .item() D2H)",
-            "prefill_s": round(steps[0], 4), "tokens": len(steps)}
+    return {"value": graphed, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+            "how": f"reference ChatGLMDecoder.generate (unmodified) driving the unmodified ChatGLM2Model wrapped in "
+                   f"chatglm_q_b200.GraphDecodeModel (static KV window, one CUDA-graph replay per token) with "
+                   f"chatglm_q_b200.install(); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after "
+                   f"the first / their summed wall time (each step: H2D token id, graph replay, top-p sampling, .item() D2H)",
+            "prefill_s": prefill_s, "tokens": n_tok,
+            "eager": {"value": eager, "prefill_s": eager_prefill,
+                      "how": "same decoder, model NOT wrapped: ~1100 eager kernels + torch.cat KV growth per token"}}
 
 
 # ----------------------------------------------------------------------------- CPU reference arm

@@ -346,3 +346,57 @@ def test_module_forward_matches_oracle():
     assert_parity(from_torch(y8), c_oracle.w8a16_gemm(a8, q8, s8, None, "float16"), "W8Linear")
     with pytest.raises(RuntimeError):  # inference only
         m4.dynamic_quant_matmul(to_torch(a, "float16").requires_grad_(), u8(bq), to_torch(s, "float16"))
+
+
+# ------------------------------------------------------------------ graph-captured decode step
+def test_graph_decode_matches_eager_reference():
+    """The CUDA-graph wrapper must reproduce the unmodified reference model token by token (greedy),
+    driven by the unmodified reference decoder loop contract: model(input_ids=, past_key_values=)."""
+    import sys
+    from pathlib import Path
+    ref = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    sys.path.insert(0, str(ref))
+    from chatglm_q.loader import create_quant_int4_model
+    from chatglm_q.model import ChatGLM2Config
+    from chatglm_q.int4.qlinear import DynamicQuantizeLinear, QEmbedding
+    from chatglm_q_b200.graph_decode import GraphDecodeModel
+    from chatglm_q_b200.install import install, uninstall
+
+    install("chatglm_q")
+    try:
+        cfg = ChatGLM2Config(hidden_size=512, inner_hidden_size=1024, head_hidden_size=64, num_multi_query_groups=2,
+                             num_attention_heads=8, num_layers=3, vocab_size=1024, max_sequence_length=256)
+        with torch.device(DEV):
+            model = create_quant_int4_model(cfg, 32, torch.float16)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        with torch.no_grad():
+            for mod in model.modules():
+                if isinstance(mod, DynamicQuantizeLinear):
+                    k, n = mod.in_features, mod.out_features
+                    w = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+                    sc = (torch.rand((k // 32, n), device=DEV, generator=g) * 0.5 + 0.75) / (4.4 * k ** 0.5)
+                    mod.apply_weights_(w, sc.half(), torch.zeros(n, device=DEV).half() if mod.bias is not None else None)
+                elif isinstance(mod, QEmbedding):
+                    mod.weight.copy_(torch.randint(0, 256, mod.weight.shape, dtype=torch.uint8, device=DEV, generator=g))
+                    mod.weight_scale.copy_((torch.rand(mod.weight_scale.shape, device=DEV, generator=g) * 0.2 + 0.05).half())
+        model.eval()
+        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
+        wrapped = GraphDecodeModel(model, max_len=64)
+        with torch.no_grad():
+            _, lg_e, kv_e = model(input_ids=prompt)
+            _, lg_g, kv_g = wrapped(input_ids=prompt, past_key_values=None)
+            assert torch.equal(lg_e, lg_g)
+            tok = lg_e[0, -1].argmax().reshape(1, 1)
+            for step in range(20):
+                _, lg_e, kv_e = model(input_ids=tok, past_key_values=kv_e)
+                _, lg_g, kv_g = wrapped(input_ids=tok, past_key_values=kv_g)
+                a, b = lg_e[0, -1].float(), lg_g[0, -1].float()
+                assert torch.isfinite(b).all()
+                err = (a - b).abs().max().item()
+                assert err <= 2e-2 * a.abs().max().item() + 1e-3, f"step {step}: logits differ by {err}"
+                assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
+                tok = a.argmax().reshape(1, 1)
+    finally:
+        uninstall("chatglm_q")
