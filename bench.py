@@ -145,6 +145,7 @@ class TokenStep:
         from chatglm_q_b200 import ops
 
         self.torch, self.ops, self.world, self.m = torch, ops, world, m
+        self.hints = int(os.environ.get("CGQ_PF_MB", "0") or 0) > 0    # experimental L2 prefetch hints: off
         self.plan, block, head = token_linears(world, rank)
         gen = torch.Generator(device=device).manual_seed(1234 + rank)
         self.layers = [[(name, *make_w4(torch, k, n, bias, device, gen)) for name, k, n, bias in block]
@@ -162,16 +163,23 @@ class TokenStep:
         dist = None
         if self.world > 1:
             import torch.distributed as dist
-        for (_, wq, sq, bq), (_, wo, so, _), (_, wi, si, _), (_, wu, su, _) in self.layers:
+        hint = ops.prefetch_next_s4 if self.hints else (lambda *a: None)
+        wl, sl, _ = self.head
+        firsts = [(l[0][1], l[0][2]) for l in self.layers[1:]] + [(wl, sl)]
+        for ((_, wq, sq, bq), (_, wo, so, _), (_, wi, si, _), (_, wu, su, _)), nxt in zip(self.layers, firsts):
+            hint(wo, so)       # each launch also streams the NEXT linear's weights into L2 (cgq_prefetch_next_w4)
             qkv = ops.dynamic_quant_matmul_s4(x, wq, sq, bias=bq)
+            hint(wi, si)
             o = ops.dynamic_quant_matmul_s4(qkv[:, :self.kq], wo, so)     # stand-in for attention out
             if dist is not None:
                 dist.all_reduce(o)
+            hint(wu, su)
             hin = ops.dynamic_quant_matmul_s4(o, wi, si)
+            hint(*nxt)
             x = ops.dynamic_quant_matmul_s4(hin[:, :self.ki], wu, su)     # stand-in for silu(h)*gate
             if dist is not None:
                 dist.all_reduce(x)
-        wl, sl, _ = self.head
+        hint(self.layers[0][0][1], self.layers[0][0][2])                  # the next token's first linear
         logits = ops.dynamic_quant_matmul_s4(x, wl, sl)
         if dist is not None:
             parts = [self.torch.empty_like(logits) for _ in range(self.world)]
@@ -285,8 +293,9 @@ def build_ref_int4_model(torch, device, seed=0):
 
 def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     """Reference ChatGLMDecoder.generate, unmodified, with this repo's kernels installed behind its QLinear
-    modules.  Headline `value`: the model object wrapped in chatglm_q_b200.GraphDecodeModel (one CUDA-graph
-    replay per token, same decoder, same model code); `eager` is the plain unwrapped model."""
+    modules.  Headline `value`: the model object wrapped in chatglm_q_b200.FusedDecodeModel (one CUDA-graph
+    replay of the fused decode step per token); `graphed_reference_forward` is the unmodified forward under a
+    CUDA graph, `eager` the plain unwrapped model."""
     if import_reference() is None:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "baseline/_ref missing: reference decoder not importable"}
@@ -328,18 +337,44 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
         rest = steps[1:]
         return round(len(rest) / sum(rest), 2), round(steps[0], 4), len(steps)
 
+    from chatglm_q_b200.fused_decode import FusedDecodeModel
+
     tok = StubTokenizer(prompt_len)
     eager, eager_prefill, _ = run(ChatGLMDecoder(cfg, model, tok, device=device, time_log=False))
-    graphed, prefill_s, n_tok = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
-                                                   tok, device=device, time_log=False))
-    del model
+    graphed, graphed_prefill, _ = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
+                                                     tok, device=device, time_log=False))
+    fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32)
+    fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+    # device time of the fused step alone (graph replays between CUDA events; the KV window is rewound so
+    # every replay attends over the same context length as the middle of the generation)
+    dev_us = None
+    if fused_model.graph is not None:
+        ctx = prompt_len + gen_tokens // 2
+        st = torch.tensor([ctx, ctx], dtype=torch.int32, device=device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        for i in range(reps + 5):
+            if i == 5:
+                e0.record()
+            fused_model.state.copy_(st, non_blocking=True)
+            fused_model.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        dev_us = round(e0.elapsed_time(e1) * 1e3 / reps, 1)
+    launches = fused_model.launches_per_step()
+    del model, fused_model
     torch.cuda.empty_cache()
-    return {"value": graphed, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
-            "how": f"reference ChatGLMDecoder.generate (unmodified) driving the unmodified ChatGLM2Model wrapped in "
-                   f"chatglm_q_b200.GraphDecodeModel (static KV window, one CUDA-graph replay per token) with "
-                   f"chatglm_q_b200.install(); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after "
-                   f"the first / their summed wall time (each step: H2D token id, graph replay, top-p sampling, .item() D2H)",
+    return {"value": fused, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+            "how": f"reference ChatGLMDecoder.generate (unmodified) driving chatglm_q_b200.FusedDecodeModel wrapped around "
+                   f"the unmodified int4g32 ChatGLM2Model (its module buffers in place): one CUDA-graph replay of {launches} "
+                   f"C-ABI launches per token (fused RMSNorm/SiLU-gate/residual dequant-matmuls + RoPE/KV/attention kernel, "
+                   f"PDL-chained); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after the first / "
+                   f"their summed wall time (each step: H2D token id, graph replay, reference top-p sampling, .item() D2H)",
             "prefill_s": prefill_s, "tokens": n_tok,
+            "fused_step_device_us": dev_us, "fused_step_launches": launches,
+            "graphed_reference_forward": {"value": graphed, "prefill_s": graphed_prefill,
+                                          "how": "same decoder, unmodified model forward captured in one CUDA graph "
+                                                 "(chatglm_q_b200.GraphDecodeModel), ~1100 kernels per token"},
             "eager": {"value": eager, "prefill_s": eager_prefill,
                       "how": "same decoder, model NOT wrapped: ~1100 eager kernels + torch.cat KV growth per token"}}
 

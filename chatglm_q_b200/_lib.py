@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libcgq.so"
@@ -22,6 +22,13 @@ SYMBOLS = {
     "cgq_w8a16_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int]),
     "cgq_debug_trace": (None, [c_void_p]),
+    "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "cgq_prefetch_next_w4": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "cgq_decode_begin_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_void_p, c_void_p]),
+    "cgq_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_int, c_void_p]),
     "cgq_w4_unpack_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cgq_w4_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cgq_w4_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -31,6 +38,7 @@ SYMBOLS = {
 }
 
 IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC, IMPL_GEMV_UMMA = 0, 1, 2, 3, 4, 5
+PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE = 0, 1, 2
 
 _lib = None
 

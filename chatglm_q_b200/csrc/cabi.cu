@@ -254,6 +254,53 @@ extern "C" int cgq_w4a16_gemm(const void* A, int64_t lda, const uint8_t* Wq, con
                            workspace_bytes, stream, CGQ_IMPL_AUTO);
 }
 
+extern "C" int cgq_prefetch_next_w4(const uint8_t* Wq, const void* scale, int N, int K) {
+  if (Wq == nullptr) {
+    set_next_w4_hint(nullptr, nullptr, 0, 0);
+    return CGQ_OK;
+  }
+  if (scale == nullptr || N <= 0 || K <= 0 || K % 32 != 0 || N % 16 != 0 ||
+      ((reinterpret_cast<uintptr_t>(Wq) | reinterpret_cast<uintptr_t>(scale)) & 15)) {
+    set_error("cgq_prefetch_next_w4: needs 16-byte aligned Wq / scale, N%%16==0, K%%32==0 (N=%d K=%d)", N, K);
+    return CGQ_ERR_MISALIGNED;
+  }
+  set_next_w4_hint(Wq, scale, N, K);
+  return CGQ_OK;
+}
+
+extern "C" int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void* scale,
+                                    const void* bias, const void* resid, void* C, int N, int K,
+                                    int group, int dtype, int prologue, const void* norm_w,
+                                    float eps, void* stream) {
+  const char* fn = "cgq_w4a16_gemv_fused";
+  const int a_len = prologue == CGQ_PRO_SILU_GATE ? 2 * K : K;
+  int rc = check_common(fn, A, a_len, Wq, scale, C, N, 1, N, K, dtype);
+  if (rc != CGQ_OK) return rc;
+  if (group != 32 || K % 32 != 0) {
+    set_error("%s: group must be 32 and divide K (group=%d, K=%d)", fn, group, K);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  if (prologue != CGQ_PRO_NONE && prologue != CGQ_PRO_RMSNORM && prologue != CGQ_PRO_SILU_GATE) {
+    set_error("%s: unknown prologue %d", fn, prologue);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  if (prologue == CGQ_PRO_RMSNORM &&
+      (norm_w == nullptr || (reinterpret_cast<uintptr_t>(norm_w) & 15))) {
+    set_error("%s: CGQ_PRO_RMSNORM needs a 16-byte aligned norm weight", fn);
+    return CGQ_ERR_MISALIGNED;
+  }
+  rc = check_device();
+  if (rc != CGQ_OK) return rc;
+  GemmArgs a{A, a_len, Wq, scale, bias, C, N, 1, N, K, dtype, nullptr,
+             static_cast<cudaStream_t>(stream)};
+  if (!w4_gemv_supported(a)) {
+    set_error("%s: needs N%%16==0 and 16-byte aligned A / Wq / scale", fn);
+    return CGQ_ERR_MISALIGNED;
+  }
+  GemvFused fu{prologue, norm_w, eps, resid};
+  return launch_w4_gemv_fused(a, fu);
+}
+
 extern "C" int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, const void* scale,
                                  const void* bias, void* C, int64_t ldc, int M, int N, int K,
                                  int dtype, void* workspace, size_t workspace_bytes, void* stream,

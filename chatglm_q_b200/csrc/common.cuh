@@ -87,7 +87,17 @@ struct GemmArgs {
   cudaStream_t stream;
 };
 
+// Fused decode-step extras of the M == 1 int4 kernel (cgq_w4a16_gemv_fused).
+struct GemvFused {
+  int prologue;        // CGQ_PRO_*
+  const void* norm_w;  // [K] RMSNorm weight (CGQ_PRO_RMSNORM)
+  float eps;
+  const void* resid;   // [N] residual added after the product is rounded, or null
+};
+
 int launch_w4_simple(const GemmArgs& a);
+int launch_w4_gemv_fused(const GemmArgs& a, const GemvFused& fu);
+void set_next_w4_hint(const void* w, const void* s, int N, int K);
 int launch_w8_simple(const GemmArgs& a);
 int launch_w4_gemv(const GemmArgs& a, bool exact);
 int launch_w4_gemv_umma(const GemmArgs& a, bool* taken);

@@ -1,0 +1,329 @@
+// Glue kernels of the fused batch-1 decode step: everything of
+// ChatGLM2Model.forward (chatglm_q/model.py:329-392) that sits BETWEEN the dequant-matmuls when one
+// new token is decoded against a KV cache.  RMSNorm, SiLU*gate and the residual adds are fused into
+// the M == 1 int4 kernel (gemv_w4.cu: cgq_w4a16_gemv_fused); what is left is
+//   * decode_begin  : QEmbedding row gather of the new token (int4/qlinear.py:122-130) + position
+//                     bookkeeping on the device (so the step is a static CUDA graph);
+//   * decode_attn   : RoPE of q/k (model.py:47-59,148-149), KV-cache append (:151-155) and the
+//                     multi-query attention of ONE query row (:157-174), one CTA per head.
+// Every kernel takes part in the programmatic-dependent-launch chain of the step: it releases its
+// dependents at once (the next dequant-matmul streams its weights while this kernel runs) and waits
+// for its producers before touching activations.
+//
+// Numerics follow the reference's rounding points for T = fp16 / bf16:
+//   rope      : complex product in fp32, rounded once to T           (torch complex-half mul = fp32 opmath)
+//   q scaling : round_T(q * (1/sqrt(d)))                             (torch divides by a scalar via the reciprocal)
+//   scores    : round_T(fp32 dot)                                    (matmul, :164)
+//   softmax   : fp32 over the scores, rounded to T                   (:168)
+//   output    : round_T(fp32 sum of p_T * v_T)                       (:171)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cgq {
+namespace {
+
+// ------------------------------------------------------------------ decode_begin
+// state[0] = tokens already in the KV cache BEFORE this step (host writes it after prefill, the kernel
+//            increments it), state[1] = the value the kernels of THIS step use.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    decode_begin_w4_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ Wq,
+                           const T* __restrict__ scale, T* __restrict__ x, int D, int group,
+                           int* __restrict__ state) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int cur = state[0];
+    state[1] = cur;
+    state[0] = cur + 1;
+  }
+  const int64_t t = ids[0];
+  const uint8_t* wrow = Wq + (t >> 1) * D;
+  const T* srow = scale + (t / group) * D;
+  const int shift = static_cast<int>(t & 1) * 4;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) x[d] = dequant4<T>((wrow[d] >> shift) & 0xF, srow[d]);
+}
+
+// ------------------------------------------------------------------ decode_attn
+struct AttnParams {
+  const void* qkv;     // [n_head*DH | n_groups*DH | n_groups*DH]
+  const void* freqs;   // [max_pos, DH] (cos, sin) pairs, second half (1, 0)  (model.py:33-43)
+  void* kcache;        // [max_len, n_groups, DH]
+  void* vcache;
+  void* out;           // [n_head*DH]
+  const int* state;
+  int n_head, n_groups, max_len;
+};
+
+constexpr int kAttnThreads = 512;
+constexpr int kAttnWarps = kAttnThreads / 32;
+constexpr int kRowsPerIter = 8;   // cache rows a warp has in flight
+
+__device__ __forceinline__ int ldcg_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <typename T, int EPL>
+__device__ __forceinline__ void load_row(const T* row, int lane, float (&f)[EPL]) {
+  if (EPL == 4) {
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(row + lane * 4));
+    const T* h = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] = DT<T>::to_f(h[e]);
+  } else {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(row + lane * 2));
+    const T* h = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) f[e] = DT<T>::to_f(h[e]);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnParams p) {
+  constexpr int EPL = DH / 32;
+  extern __shared__ float sm[];
+  float* q_s = sm;                     // rotated, scaled query (T-rounded values)
+  float* k_s = q_s + DH;               // rotated new key
+  float* v_s = k_s + DH;               // new value
+  float* red = v_s + DH;               // [kAttnWarps][DH]
+  float* wred = red + kAttnWarps * DH; // [kAttnWarps]
+  float* sc = wred + kAttnWarps;       // [n_past + 1] scores / probabilities
+
+  const int h = blockIdx.x;
+  const int hpg = p.n_head / p.n_groups;
+  const int g = h / hpg;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait_prior_grid();
+
+  const int n_past = ldcg_i32(p.state + 1);
+  if (n_past >= p.max_len) return;     // window exhausted: the host never launches in this state
+  const T* qkv = static_cast<const T*>(p.qkv);
+  const T* fr = static_cast<const T*>(p.freqs) + static_cast<size_t>(n_past + 1) * DH;  // position id = n_past + 1
+  T* kc = static_cast<T*>(p.kcache);
+  T* vc = static_cast<T*>(p.vcache);
+  const size_t row_stride = static_cast<size_t>(p.n_groups) * DH;
+  const bool writer = (h % hpg) == 0;
+
+  if (t < DH) {
+    // rope of pair j of q (t < DH/2) or k (t >= DH/2)
+    const bool is_q = t < DH / 2;
+    const int j = is_q ? t : t - DH / 2;
+    const T* src = is_q ? qkv + h * DH : qkv + (p.n_head + g) * DH;
+    const float a = DT<T>::to_f(src[2 * j]), b = DT<T>::to_f(src[2 * j + 1]);
+    const float c = DT<T>::to_f(fr[2 * j]), s = DT<T>::to_f(fr[2 * j + 1]);
+    const T re = DT<T>::from_f(a * c - b * s);
+    const T im = DT<T>::from_f(a * s + b * c);
+    if (is_q) {
+      const float inv = 1.0f / sqrtf(static_cast<float>(DH));
+      q_s[2 * j] = DT<T>::to_f(DT<T>::from_f(DT<T>::to_f(re) * inv));
+      q_s[2 * j + 1] = DT<T>::to_f(DT<T>::from_f(DT<T>::to_f(im) * inv));
+    } else {
+      k_s[2 * j] = DT<T>::to_f(re);
+      k_s[2 * j + 1] = DT<T>::to_f(im);
+      if (writer) {
+        kc[n_past * row_stride + g * DH + 2 * j] = re;
+        kc[n_past * row_stride + g * DH + 2 * j + 1] = im;
+      }
+    }
+  } else if (t < 2 * DH) {
+    const int d = t - DH;
+    const T v = qkv[(p.n_head + p.n_groups + g) * DH + d];
+    v_s[d] = DT<T>::to_f(v);
+    if (writer) vc[n_past * row_stride + g * DH + d] = v;
+  }
+  __syncthreads();
+
+  // ---- scores over the cached rows (one warp per row, kRowsPerIter rows in flight) + the new row
+  float qr[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) qr[e] = q_s[lane * EPL + e];
+  const T* kbase = kc + g * DH;
+  for (int l0 = warp; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
+    float kr[kRowsPerIter][EPL];
+#pragma unroll
+    for (int i = 0; i < kRowsPerIter; ++i) {
+      const int l = l0 + i * kAttnWarps;
+      if (l < n_past) load_row<T, EPL>(kbase + l * row_stride, lane, kr[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerIter; ++i) {
+      const int l = l0 + i * kAttnWarps;
+      if (l < n_past) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[i][e], d);
+        d = warp_sum(d);
+        if (lane == 0) sc[l] = DT<T>::to_f(DT<T>::from_f(d));
+      }
+    }
+  }
+  if (warp == 0) {
+    float d = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], k_s[lane * EPL + e], d);
+    d = warp_sum(d);
+    if (lane == 0) sc[n_past] = DT<T>::to_f(DT<T>::from_f(d));
+  }
+  __syncthreads();
+
+  // ---- softmax in fp32 over n = n_past + 1 scores, probabilities rounded to T
+  const int n = n_past + 1;
+  float mx = -INFINITY;
+  for (int l = t; l < n; l += kAttnThreads) mx = fmaxf(mx, sc[l]);
+  mx = warp_max(mx);
+  if (lane == 0) wred[warp] = mx;
+  __syncthreads();
+  mx = wred[0];
+#pragma unroll
+  for (int w = 1; w < kAttnWarps; ++w) mx = fmaxf(mx, wred[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int l = t; l < n; l += kAttnThreads) {
+    const float e = expf(sc[l] - mx);
+    sc[l] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) wred[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kAttnWarps; ++w) sum += wred[w];
+  for (int l = t; l < n; l += kAttnThreads) sc[l] = DT<T>::to_f(DT<T>::from_f(sc[l] / sum));
+  __syncthreads();
+
+  // ---- out = p · V
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  const T* vbase = vc + g * DH;
+  for (int l0 = warp; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
+    float vr[kRowsPerIter][EPL];
+#pragma unroll
+    for (int i = 0; i < kRowsPerIter; ++i) {
+      const int l = l0 + i * kAttnWarps;
+      if (l < n_past) load_row<T, EPL>(vbase + l * row_stride, lane, vr[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerIter; ++i) {
+      const int l = l0 + i * kAttnWarps;
+      if (l < n_past) {
+        const float pl = sc[l];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[i][e], acc[e]);
+      }
+    }
+  }
+  if (warp == 0) {
+    const float pl = sc[n_past];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, v_s[lane * EPL + e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) red[warp * DH + lane * EPL + e] = acc[e];
+  __syncthreads();
+  if (t < DH) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) o += red[w * DH + t];
+    static_cast<T*>(p.out)[h * DH + t] = DT<T>::from_f(o);
+  }
+}
+
+template <typename K, typename... Args>
+int launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
+  return CGQ_OK;
+}
+
+template <typename T, int DH>
+int launch_attn(const AttnParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (3 * DH + kAttnWarps * DH + kAttnWarps + p.max_len + 1);
+  auto kern = decode_attn_kernel<T, DH>;
+  if (smem > 48 * 1024)
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  return launch_pdl(kern, dim3(p.n_head), dim3(kAttnThreads), smem, st, p);
+}
+
+}  // namespace
+}  // namespace cgq
+
+using namespace cgq;
+
+extern "C" int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq, const void* scale, void* x,
+                                   int V, int D, int group, int dtype, int* state, void* stream) {
+  if (V <= 0 || D <= 0 || group <= 0 || (group & 1) || V % group != 0 || ids == nullptr ||
+      Wq == nullptr || scale == nullptr || x == nullptr || state == nullptr) {
+    set_error("cgq_decode_begin_w4: bad arguments V=%d D=%d group=%d", V, D, group);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((D + 255) / 256), block(256);
+  if (dtype == CGQ_DTYPE_F16)
+    return launch_pdl(decode_begin_w4_kernel<__half>, grid, block, 0, st, ids, Wq,
+                      static_cast<const __half*>(scale), static_cast<__half*>(x), D, group, state);
+  if (dtype == CGQ_DTYPE_BF16)
+    return launch_pdl(decode_begin_w4_kernel<__nv_bfloat16>, grid, block, 0, st, ids, Wq,
+                      static_cast<const __nv_bfloat16*>(scale), static_cast<__nv_bfloat16*>(x), D,
+                      group, state);
+  set_error("cgq_decode_begin_w4: bad dtype %d", dtype);
+  return CGQ_ERR_BAD_DTYPE;
+}
+
+extern "C" int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void* vcache,
+                                    void* out, const int* state, int n_head, int n_groups,
+                                    int d_head, int max_len, int dtype, void* stream) {
+  if (n_head <= 0 || n_groups <= 0 || n_head % n_groups != 0 || max_len <= 0 ||
+      (d_head != 64 && d_head != 128)) {
+    set_error("cgq_decode_attention: bad shape n_head=%d n_groups=%d d_head=%d (64 or 128) max_len=%d",
+              n_head, n_groups, d_head, max_len);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  if (max_len > 32768) {
+    set_error("cgq_decode_attention: max_len %d exceeds the single-CTA score buffer (32768)", max_len);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  if (qkv == nullptr || freqs == nullptr || kcache == nullptr || vcache == nullptr ||
+      out == nullptr || state == nullptr ||
+      ((reinterpret_cast<uintptr_t>(kcache) | reinterpret_cast<uintptr_t>(vcache)) & 7)) {
+    set_error("cgq_decode_attention: null or misaligned pointer");
+    return CGQ_ERR_MISALIGNED;
+  }
+  AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == CGQ_DTYPE_F16)
+    return d_head == 128 ? launch_attn<__half, 128>(p, st) : launch_attn<__half, 64>(p, st);
+  if (dtype == CGQ_DTYPE_BF16)
+    return d_head == 128 ? launch_attn<__nv_bfloat16, 128>(p, st)
+                         : launch_attn<__nv_bfloat16, 64>(p, st);
+  set_error("cgq_decode_attention: bad dtype %d", dtype);
+  return CGQ_ERR_BAD_DTYPE;
+}

@@ -50,9 +50,12 @@ constexpr int kThreads = (CW + 1) * 32;
 template <bool kM1>
 struct Cfg {
   static constexpr int MR = kM1 ? 1 : MMAX;           // token rows staged / reduced
-  static constexpr int A_BYTES = MR * A_STRIDE;
+  // M == 1: the activation band of the CTA is staged ONCE by the consumer warps (plain L2 loads right
+  // after the dependency wait, optionally through a fused prologue), not per stage through TMA
+  static constexpr int A_BYTES = kM1 ? 0 : MR * A_STRIDE;
   static constexpr int RED_BYTES = CW * MR * BN * 4;
-  static constexpr int XRED_BYTES = 8 * MR * BN * 4;   // band sums of up to 8 cluster ranks (rank 0)
+  // band sums of the Z cluster ranks, received by rank 0 (same layout in every CTA of the cluster)
+  __host__ __device__ static constexpr int xred_bytes(int Z) { return Z > 1 ? Z * MR * BN * 4 : 0; }
   static constexpr int STAGE_BYTES = W_BYTES + S_BYTES + A_BYTES;
 };
 
@@ -116,7 +119,106 @@ struct Params {
   int Z;       // k-bands per tile == cluster size
   int S;       // ring depth
   unsigned long long* trace;  // optional timeline (cgq_debug_trace), 8 words per CTA
+  // fused decode-step pieces (M == 1 only; cgq_w4a16_gemv_fused)
+  const void* resid;   // [N] or null: C = resid + round(acc) (+bias)   (model.py:243,246 `x = x + h`)
+  const void* norm_w;  // [K] RMSNorm weight (PRO_RMSNORM)
+  float eps;
+  int band_units;      // k-stages of activation band staged per CTA (max over the cluster ranks)
+  // L2 prefetch of the NEXT decode launch's weights (cgq_prefetch_next_w4): the first pf_depth k-stages
+  // of each of its pf_Z bands, in the lockstep order that launch will read them
+  const uint8_t* pf_w;
+  const uint8_t* pf_s;   // scales, 2 bytes per element
+  int pf_N, pf_rows, pf_groups, pf_SPT, pf_Z, pf_depth, pf_ppc_w, pf_ppc, pf_pieces;
 };
+constexpr int kPfPiece = 16384;
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// piece `idx` of the next launch's weight stream -> one bulk L2 prefetch
+__device__ __forceinline__ void prefetch_piece(const Params& p, int idx) {
+  const int chunk = idx / p.pf_ppc, j = idx - chunk * p.pf_ppc;
+  const int i = chunk / p.pf_Z, z = chunk - i * p.pf_Z;
+  const int u = p.pf_SPT * z / p.pf_Z + i;
+  if (u >= p.pf_SPT * (z + 1) / p.pf_Z) return;
+  if (j < p.pf_ppc_w) {
+    const int row0 = u * ROWS;
+    const int64_t bytes = static_cast<int64_t>(min(ROWS, p.pf_rows - row0)) * p.pf_N;
+    const int64_t off = static_cast<int64_t>(j) * kPfPiece;
+    if (off < bytes)
+      prefetch_l2_bulk(p.pf_w + static_cast<int64_t>(row0) * p.pf_N + off,
+                       static_cast<uint32_t>(bytes - off < kPfPiece ? bytes - off : kPfPiece));
+  } else {
+    const int g0 = u * CW;
+    const int64_t bytes = static_cast<int64_t>(min(CW, p.pf_groups - g0)) * p.pf_N * 2;
+    const int64_t off = static_cast<int64_t>(j - p.pf_ppc_w) * kPfPiece;
+    if (off < bytes)
+      prefetch_l2_bulk(p.pf_s + static_cast<int64_t>(g0) * p.pf_N * 2 + off,
+                       static_cast<uint32_t>(bytes - off < kPfPiece ? bytes - off : kPfPiece));
+  }
+}
+
+enum { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SILU_GATE = 2 };
+
+__device__ __forceinline__ uint4 ldcg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldnc128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ float sumsq8(const uint4& v) {
+  const T* h = reinterpret_cast<const T*>(&v);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float f = DT<T>::to_f(h[j]);
+    s = fmaf(f, f, s);
+  }
+  return s;
+}
+// RMSNorm of 8 elements, the reference's roundings: round_T(x * rstd) then round_T(. * w)
+// (chatglm_q/model.py:68-73: `_norm(x.float()).type_as(x)`, then `output * self.weight`).
+template <typename T>
+__device__ __forceinline__ uint4 rmsnorm8(const uint4& x, const uint4& w, float rstd) {
+  uint4 o;
+  const T* xh = reinterpret_cast<const T*>(&x);
+  const T* wh = reinterpret_cast<const T*>(&w);
+  T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const T n = DT<T>::from_f(DT<T>::to_f(xh[j]) * rstd);
+    oh[j] = DT<T>::from_f(DT<T>::to_f(n) * DT<T>::to_f(wh[j]));
+  }
+  return o;
+}
+// SwiGLU of 8 elements: round_T(round_T(silu(h)) * gate)  (model.py:200-201, F.silu computes in fp32)
+template <typename T>
+__device__ __forceinline__ uint4 silu_gate8(const uint4& h, const uint4& g) {
+  uint4 o;
+  const T* hh = reinterpret_cast<const T*>(&h);
+  const T* gh = reinterpret_cast<const T*>(&g);
+  T* oh = reinterpret_cast<T*>(&o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = DT<T>::to_f(hh[j]);
+    const T act = DT<T>::from_f(x / (1.f + expf(-x)));
+    oh[j] = DT<T>::from_f(DT<T>::to_f(act) * DT<T>::to_f(gh[j]));
+  }
+  return o;
+}
+template <typename T>
+__device__ __forceinline__ T add_resid(T c, const T* resid, int n) {
+  return resid == nullptr ? c : DT<T>::from_f(DT<T>::to_f(resid[n]) + DT<T>::to_f(c));
+}
 
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
   if (p.trace != nullptr && blockIdx.x < 1024) {
@@ -126,7 +228,7 @@ __device__ __forceinline__ void stamp(const Params& p, int slot) {
   }
 }
 
-template <typename T, bool kTrick, bool kM1>
+template <typename T, bool kTrick, bool kM1, int kPro>
 __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     w4_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmS,
                    const Params p) {
@@ -142,8 +244,11 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   const uint32_t off_red = S * C::STAGE_BYTES;
   float* red = reinterpret_cast<float*>(gen + off_red);
   float* xred = reinterpret_cast<float*>(gen + off_red + C::RED_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES + C::XRED_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES + C::xred_bytes(p.Z));
   uint64_t* empty = full + S;
+  // M == 1: activation band of this CTA (band_units x 128 k, zero beyond K), staged by the consumers
+  const uint32_t off_band = (off_red + C::RED_BYTES + C::xred_bytes(p.Z) + 16u * S + 15u) & ~15u;
+  const uint32_t Aband = base + off_band;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Z = p.Z;
@@ -178,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       auto issue_w = [&](int i, int slot) {
         const int ks = u0 + i;
         const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
-        ptx::mbar_expect_tx(&full[slot], W_BYTES + S_BYTES + p.M * kvalid * 2);
+        ptx::mbar_expect_tx(&full[slot], W_BYTES + S_BYTES + (kM1 ? 0 : p.M * kvalid * 2));
         ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, tile * BN, ks * ROWS, &full[slot], pol);
         ptx::tma_load_2d(gen + S * W_BYTES + slot * S_BYTES, &tmS, tile * BN, ks * CW, &full[slot],
                          pol);
@@ -187,35 +292,109 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         const int ks = u0 + i;
         const int kvalid = min(KSTAGE, p.K - ks * KSTAGE);
         uint8_t* dst = gen + S * (W_BYTES + S_BYTES) + slot * C::A_BYTES;
-        if (kM1) {
-          ptx::bulk_load_1d(dst, A + ks * KSTAGE, kvalid * 2, &full[slot]);
-        } else {
-          for (int m = 0; m < p.M; ++m)
-            ptx::bulk_load_1d(dst + m * A_STRIDE, A + m * p.lda + ks * KSTAGE, kvalid * 2,
-                              &full[slot]);
-        }
+        for (int m = 0; m < p.M; ++m)
+          ptx::bulk_load_1d(dst + m * A_STRIDE, A + m * p.lda + ks * KSTAGE, kvalid * 2,
+                            &full[slot]);
       };
       const int prefill = min(n_units, S);
       // weights do not depend on the previous kernel: start streaming them before the PDL wait
       for (int i = 0; i < prefill; ++i) issue_w(i, i);
-      ptx::pdl_wait_prior_grid();
-      for (int i = 0; i < prefill; ++i) issue_a(i, i);
+      if (!kM1) {
+        ptx::pdl_wait_prior_grid();
+        for (int i = 0; i < prefill; ++i) issue_a(i, i);
+      }
+      // next launch's weights -> L2, spread over this CTA's refill iterations (own loads first)
+      int pf_next = blockIdx.x;
+      const int pf_mine = p.pf_pieces > 0 ? (p.pf_pieces - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int pf_iters = n_units - prefill;
+      const int pf_per = pf_iters > 0 ? (pf_mine + pf_iters - 1) / pf_iters : pf_mine;
+      auto pf_issue = [&](int count) {
+        for (int c = 0; c < count && pf_next < p.pf_pieces; ++c, pf_next += gridDim.x)
+          prefetch_piece(p, pf_next);
+      };
+      if (pf_iters <= 0) pf_issue(pf_mine);
       int slot = 0, phase = 1;
       for (int i = prefill; i < n_units; ++i) {
         ptx::mbar_wait(&empty[slot], phase ^ 1);
         issue_w(i, slot);
-        issue_a(i, slot);
+        if (!kM1) issue_a(i, slot);
+        pf_issue(pf_per);
         if (++slot == S) {
           slot = 0;
           phase ^= 1;
         }
       }
+      pf_issue(pf_mine);
     }
     __syncwarp();
   } else {
   // =========================== consumers ===========================
-  ptx::pdl_wait_prior_grid();
-  if (threadIdx.x == 0) stamp(p, 2);
+  if (kM1) {
+    // ---- stage the activation band (16-byte chunks of 8 k) with the fused prologue
+    const int tid = threadIdx.x;                 // 0 .. CW*32-1
+    const int nchunk = p.K >> 3;                 // valid chunks of the activation row
+    const int c_lo = u0 * (KSTAGE / 8), c_hi = u1 * (KSTAGE / 8);
+    for (int c = c_lo + tid; c < c_hi; c += CW * 32)
+      if (c >= nchunk) ptx::sts128(Aband + (c - c_lo) * 16, make_uint4(0, 0, 0, 0));
+    if (kPro == PRO_RMSNORM) {
+      // every CTA needs sum(x^2) over the WHOLE row (8 KB from L2 at K=4096) but normalises only its
+      // band; the chunks a thread loads for the sum stay in registers and are the ones it normalises
+      constexpr int U = 4;
+      const bool single = nchunk <= U * CW * 32;
+      const T* nw = static_cast<const T*>(p.norm_w);
+      uint4 xr[U], wr[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {  // the norm weight does not depend on the previous kernel
+        const int c = tid + CW * 32 * i;
+        wr[i] = (single && c >= c_lo && c < c_hi && c < nchunk) ? ldnc128(nw + c * 8)
+                                                                : make_uint4(0, 0, 0, 0);
+      }
+      ptx::pdl_wait_prior_grid();
+      if (threadIdx.x == 0) stamp(p, 2);
+      float ss = 0.f;
+      for (int cb = 0; cb < nchunk; cb += U * CW * 32) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int c = cb + tid + CW * 32 * i;
+          xr[i] = c < nchunk ? ldcg128(A + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) ss += sumsq8<T>(xr[i]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) red[warp] = ss;
+      ptx::named_bar_sync(1, CW * 32);
+      float tot_ss = 0.f;
+#pragma unroll
+      for (int w = 0; w < CW; ++w) tot_ss += red[w];
+      const float rstd = rsqrtf(tot_ss / static_cast<float>(p.K) + p.eps);
+      if (single) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int c = tid + CW * 32 * i;
+          if (c >= c_lo && c < c_hi && c < nchunk)
+            ptx::sts128(Aband + (c - c_lo) * 16, rmsnorm8<T>(xr[i], wr[i], rstd));
+        }
+      } else {
+        for (int c = c_lo + tid; c < c_hi && c < nchunk; c += CW * 32)
+          ptx::sts128(Aband + (c - c_lo) * 16,
+                      rmsnorm8<T>(ldcg128(A + c * 8), ldnc128(nw + c * 8), rstd));
+      }
+    } else {
+      ptx::pdl_wait_prior_grid();
+      if (threadIdx.x == 0) stamp(p, 2);
+      for (int c = c_lo + tid; c < c_hi && c < nchunk; c += CW * 32) {
+        uint4 v = ldcg128(A + c * 8);
+        if (kPro == PRO_SILU_GATE) v = silu_gate8<T>(v, ldcg128(A + p.K + c * 8));
+        ptx::sts128(Aband + (c - c_lo) * 16, v);
+      }
+    }
+    ptx::named_bar_sync(1, CW * 32);
+  } else {
+    ptx::pdl_wait_prior_grid();
+    if (threadIdx.x == 0) stamp(p, 2);
+  }
   const int g = lane >> 2, tig = lane & 3;
   constexpr int NT = kM1 ? 2 : 4;  // accumulator registers kept per MMA tile
   float tot[8][NT];
@@ -231,7 +410,8 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     if (it == 0 && threadIdx.x == 0) stamp(p, 3);
     const uint32_t wrow = Wsm + slot * W_BYTES + (16 * warp) * BN;
     const uint32_t srow = Ssm + slot * S_BYTES + warp * (BN * 2) + g * 32;
-    const uint32_t arow = Asm + slot * C::A_BYTES + (kM1 ? 0 : g * A_STRIDE) + (32 * warp + 4 * tig) * 2;
+    const uint32_t arow = kM1 ? Aband + (it * KSTAGE + 32 * warp + 4 * tig) * 2
+                              : Asm + slot * C::A_BYTES + g * A_STRIDE + (32 * warp + 4 * tig) * 2;
 
     float grp[8][4];
     float ag[4];
@@ -354,7 +534,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         const T* bias = static_cast<const T*>(p.bias);
 #pragma unroll
         for (int m = 0; m < MR; ++m)
-          if (m < p.M) Cp[m * p.ldc + n] = epilogue<T>(v[m], bias, n);
+          if (m < p.M)
+            Cp[m * p.ldc + n] = add_resid<T>(epilogue<T>(v[m], bias, n),
+                                             kM1 ? static_cast<const T*>(p.resid) : nullptr, n);
       }
     } else {
       // push the band sum into rank 0's shared memory (DSMEM); rank 0 adds them in rank order
@@ -379,7 +561,8 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
           if (m < p.M) {
             float acc = 0.f;
             for (int zz = 0; zz < Z; ++zz) acc += xred[(zz * MR + m) * BN + t];
-            Cp[m * p.ldc + n] = epilogue<T>(acc, bias, n);
+            Cp[m * p.ldc + n] = add_resid<T>(epilogue<T>(acc, bias, n),
+                                             kM1 ? static_cast<const T*>(p.resid) : nullptr, n);
           }
         }
       }
@@ -397,19 +580,46 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return v;
 }
 
-template <typename T, bool kTrick, bool kM1>
+// (k-stages per tile, k-bands per tile == cluster size) of a decode launch
+void plan_bands(int N, int K, int* SPT_out, int* Z_out) {
+  static const int z_env = env_int("CGQ_GEMV_Z", 0, 0, 8);
+  static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 4, 1, 4);
+  const int SPT = (K / 32 + CW - 1) / CW;
+  const int tiles = (N + BN - 1) / BN;
+  const int slots = cps * sm_count();
+  // fill the CTA slots of the SMs in one wave, powers of two up to the portable cluster size, never
+  // more bands than k-stages
+  int Z = 1;
+  while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
+  if (z_env > 0) Z = z_env;
+  if (Z > SPT) Z = 1;
+  *SPT_out = SPT;
+  *Z_out = Z;
+}
+
+struct NextHint {
+  const void* w;
+  const void* s;
+  int N, K;
+};
+thread_local NextHint g_next = {nullptr, nullptr, 0, 0};
+
+template <typename T, bool kTrick, bool kM1, int kPro>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
                 int grid, int stages, bool pdl) {
   using C = Cfg<kM1>;
   const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
-                      C::XRED_BYTES + 16 * stages + 16;
-  auto kern = w4_gemv_kernel<T, kTrick, kM1>;
+                      C::xred_bytes(prm.Z) + 16 * stages + 32 +
+                      (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
+  auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro>;
   static size_t configured[64] = {0};
   int dev = 0;
   CGQ_CUDA_TRY(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && smem > configured[dev]) {
     CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
     configured[dev] = smem;
   }
   cudaLaunchConfig_t cfg = {};
@@ -437,22 +647,29 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
   return CGQ_OK;
 }
 
+template <typename T, bool kTrick>
+int launch_m1(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, const Params& prm,
+              int grid, int stages, bool pdl, int pro) {
+  switch (pro) {
+    case PRO_RMSNORM:
+      return launch_inst<T, kTrick, true, PRO_RMSNORM>(a, tmW, tmS, prm, grid, stages, pdl);
+    case PRO_SILU_GATE:
+      return launch_inst<T, kTrick, true, PRO_SILU_GATE>(a, tmW, tmS, prm, grid, stages, pdl);
+    default:
+      return launch_inst<T, kTrick, true, PRO_NONE>(a, tmW, tmS, prm, grid, stages, pdl);
+  }
+}
+
 template <typename T>
-int launch_t(const GemmArgs& a, bool exact) {
+int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
   const int G = a.K / 32;
-  const int SPT = (G + CW - 1) / CW;
   const int tiles = (a.N + BN - 1) / BN;
   static const int stages_env = env_int("CGQ_GEMV_STAGES", 0, 0, 16);
-  static const int z_env = env_int("CGQ_GEMV_Z", 0, 0, 8);
   static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
-  // k-bands per tile: fill the CTA slots of the SMs in one wave, powers of two up to the portable
-  // cluster size, never more bands than k-stages
   static const int cps = env_int("CGQ_GEMV_CTAS_PER_SM", 4, 1, 4);
   const int slots = cps * sm_count();
-  int Z = 1;
-  while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
-  if (z_env > 0) Z = z_env;
-  if (Z > SPT) Z = 1;
+  int SPT, Z;
+  plan_bands(a.N, a.K, &SPT, &Z);
   const int grid = tiles * Z;
   // fewer CTAs than slots -> deeper rings keep the same number of bytes in flight
   int stages = stages_env > 0 ? stages_env : (grid * 4 <= slots * 3 ? 6 : 4);
@@ -486,15 +703,46 @@ int launch_t(const GemmArgs& a, bool exact) {
   prm.Z = Z;
   prm.S = stages;
   prm.trace = static_cast<unsigned long long*>(take_trace_buffer());
+  prm.resid = fu != nullptr ? fu->resid : nullptr;
+  prm.norm_w = fu != nullptr ? fu->norm_w : nullptr;
+  prm.eps = fu != nullptr ? fu->eps : 0.f;
+  prm.band_units = per_cta;
+  const int pro = fu != nullptr ? fu->prologue : PRO_NONE;
+  // one-shot hint: stream the next launch's weights into L2 from this kernel's producers
+  const NextHint nh = g_next;
+  g_next = NextHint{nullptr, nullptr, 0, 0};
+  prm.pf_pieces = 0;
+  static const int pf_mb = env_int("CGQ_PF_MB", 0, 0, 512);   // measured slower on B200: off unless asked for
+  if (nh.w != nullptr && pf_mb > 0) {
+    int spt_n, z_n;
+    plan_bands(nh.N, nh.K, &spt_n, &z_n);
+    const int per_n = (spt_n + z_n - 1) / z_n;
+    const int64_t stage_bytes = static_cast<int64_t>(ROWS + CW * 2) * nh.N;   // weights + scales of one k-stage
+    int64_t depth = (static_cast<int64_t>(pf_mb) << 20) / (stage_bytes * z_n);
+    if (depth > per_n) depth = per_n;
+    if (depth > 0) {
+      prm.pf_w = static_cast<const uint8_t*>(nh.w);
+      prm.pf_s = static_cast<const uint8_t*>(nh.s);
+      prm.pf_N = nh.N;
+      prm.pf_rows = nh.K / 2;
+      prm.pf_groups = nh.K / 32;
+      prm.pf_SPT = spt_n;
+      prm.pf_Z = z_n;
+      prm.pf_depth = static_cast<int>(depth);
+      prm.pf_ppc_w = (ROWS * nh.N + kPfPiece - 1) / kPfPiece;
+      prm.pf_ppc = prm.pf_ppc_w + (CW * 2 * nh.N + kPfPiece - 1) / kPfPiece;
+      prm.pf_pieces = static_cast<int>(depth) * z_n * prm.pf_ppc;
+    }
+  }
 
   constexpr bool kIsHalf = (DT<T>::code == CGQ_DTYPE_F16);
   const bool trick = kIsHalf && !exact;
   if (a.M == 1) {
-    if (trick) return launch_inst<T, kIsHalf, true>(a, tmW, tmS, prm, grid, stages, pdl);
-    return launch_inst<T, false, true>(a, tmW, tmS, prm, grid, stages, pdl);
+    if (trick) return launch_m1<T, kIsHalf>(a, tmW, tmS, prm, grid, stages, pdl, pro);
+    return launch_m1<T, false>(a, tmW, tmS, prm, grid, stages, pdl, pro);
   }
-  if (trick) return launch_inst<T, kIsHalf, false>(a, tmW, tmS, prm, grid, stages, pdl);
-  return launch_inst<T, false, false>(a, tmW, tmS, prm, grid, stages, pdl);
+  if (trick) return launch_inst<T, kIsHalf, false, PRO_NONE>(a, tmW, tmS, prm, grid, stages, pdl);
+  return launch_inst<T, false, false, PRO_NONE>(a, tmW, tmS, prm, grid, stages, pdl);
 }
 
 }  // namespace
@@ -512,7 +760,18 @@ int launch_w4_gemv(const GemmArgs& a, bool exact) {
     const int rc = launch_w4_gemv_umma(a, &taken);
     if (rc != CGQ_OK || taken) return rc;
   }
-  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, exact) : launch_t<__nv_bfloat16>(a, exact);
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, exact, nullptr)
+                                  : launch_t<__nv_bfloat16>(a, exact, nullptr);
+}
+
+void set_next_w4_hint(const void* w, const void* s, int N, int K) {
+  g_next = NextHint{w, s, N, K};
+}
+
+// M == 1 with a fused prologue (RMSNorm / SiLU-gate on the activation) and residual epilogue.
+int launch_w4_gemv_fused(const GemmArgs& a, const GemvFused& fu) {
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, false, &fu)
+                                  : launch_t<__nv_bfloat16>(a, false, &fu);
 }
 
 }  // namespace cgq

@@ -1,0 +1,216 @@
+"""Fused batch-1 decode step behind `ChatGLM2Model.forward`'s call signature.
+
+`ChatGLMDecoder.generate` (chatglm_q/decoder.py:76-97) calls `model(input_ids=..., past_key_values=...)`
+once per token.  `FusedDecodeModel` wraps the SAME int4 model object (its module buffers are used in
+place, nothing is re-packed or copied) and answers a one-token call with ONE CUDA-graph replay of
+5 x n_layers + 2 launches of this repo's kernels through the C-ABI (include/cgq.h):
+
+    cgq_decode_begin_w4                       word_embedding row of the token, position bookkeeping
+    per layer (chatglm_q/model.py:230-246):
+      cgq_w4a16_gemv_fused  RMSNORM, bias     attn_ln + qkv_proj            (:231, :139)
+      cgq_decode_attention                    RoPE, KV append, attention    (:140-174)
+      cgq_w4a16_gemv_fused  resid             o_proj, x = x + h             (:175, :243)
+      cgq_w4a16_gemv_fused  RMSNORM           ffn_ln + w_in                 (:244, :200)
+      cgq_w4a16_gemv_fused  SILU_GATE, resid  silu(h)*gate, w_out, x + h    (:201, :246)
+    cgq_w4a16_gemv_fused  RMSNORM             final_ln + lm_head            (:381-382)
+
+All launches are chained with programmatic dependent launch: each dequant-matmul streams its weights
+from HBM while the kernel before it is still running.  The KV cache is a static `[max_len, groups, d]`
+buffer per layer in the reference's own `past_key_values` layout; the position lives on the device so
+the graph is static.  Prefill (more than one token, or no cache) runs the unmodified model (whose
+linears are this repo's tcgen05 kernels after `install()`); when the static window is exhausted the
+wrapper falls back to the unmodified model with an exported cache (correct, just not fused).
+
+torch is used for device memory and the graph capture only.  There is no CPU / eager fallback for
+the fused step itself: a model this path cannot take (int8, fp32, other head sizes) raises TypeError
+at construction — use `GraphDecodeModel` for those.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE
+
+_DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
+
+
+class _FusedCache:
+    """Opaque `past_key_values` handle returned to the decoder (the state lives in the wrapper)."""
+
+    def __init__(self, owner: "FusedDecodeModel"):
+        self.owner = owner
+
+
+def _is_w4_linear(m) -> bool:
+    w, s = getattr(m, "weight", None), getattr(m, "weight_scale", None)
+    return (isinstance(w, Tensor) and isinstance(s, Tensor) and w.dtype == torch.uint8 and w.dim() == 2
+            and s.dim() == 2 and s.shape[1] == w.shape[1] and w.shape[0] * 2 == s.shape[0] * 32)
+
+
+class FusedDecodeModel:
+    def __init__(self, model: torch.nn.Module, max_len: int = 1024):
+        cfg = model.config
+        self.model = model
+        self.cfg = cfg
+        self.max_len = int(min(max_len, cfg.max_sequence_length - 1))   # row max_len of freqs_cis_cache is read
+        self.graph: torch.cuda.CUDAGraph | None = None
+        self.n_valid = 0
+        self._eager_kv = None
+        self._ready = False
+        self.hints = int(os.environ.get("CGQ_PF_MB", "0") or 0) > 0
+        lins = [model.lm_head]
+        for layer in model.layers:
+            lins += [layer.attn.qkv_proj, layer.attn.o_proj, layer.ffn.w_in, layer.ffn.w_out]
+        if not all(_is_w4_linear(m) for m in lins):
+            raise TypeError("FusedDecodeModel needs the int4g32 model (uint8 [K/2,N] weights, [K/32,N] scales)")
+        emb = model.word_embedding
+        if not (isinstance(getattr(emb, "weight", None), Tensor) and emb.weight.dtype == torch.uint8
+                and hasattr(emb, "weight_scale")):
+            raise TypeError("FusedDecodeModel needs the int4 QEmbedding word_embedding")
+        dt = model.lm_head.weight_scale.dtype
+        if dt not in _DTYPE_CODE:
+            raise TypeError(f"FusedDecodeModel computes in float16 / bfloat16, model is {dt}")
+        if cfg.head_hidden_size not in (64, 128):
+            raise TypeError("FusedDecodeModel attention kernel is built for head sizes 64 and 128")
+        self.dtype = dt
+        self.code = _DTYPE_CODE[dt]
+
+    # nn.Module-ish surface the decoder / loader touch
+    def __getattr__(self, name):
+        return getattr(self.model, name)
+
+    def to(self, *a, **k):
+        self.model.to(*a, **k)
+        self._ready = False
+        return self
+
+    # ---------------------------------------------------------------- static buffers
+    def _setup(self, device: torch.device):
+        cfg, dt = self.cfg, self.dtype
+        H, DH, NH, NG = cfg.hidden_size, cfg.head_hidden_size, cfg.num_attention_heads, cfg.num_multi_query_groups
+        z = lambda *shape, dtype=dt: torch.zeros(shape, device=device, dtype=dtype)  # noqa: E731
+        self.ids = z(1, 1, dtype=torch.long)
+        self.state = z(2, dtype=torch.int32)
+        self.x = z(H)
+        self.qkv = z(DH * (NH + 2 * NG))
+        self.ao = z(DH * NH)
+        self.u = z(2 * cfg.inner_hidden_size)
+        self.logits = z(1, 1, cfg.vocab_size)
+        # the reference's past_key_values layout (n_batch, n_past, n_groups, 1, d_head), model.py:347-349
+        self.kv = tuple((z(1, self.max_len, NG, 1, DH), z(1, self.max_len, NG, 1, DH)) for _ in range(cfg.num_layers))
+        self.freqs = self.model.freqs_cis_cache
+        assert self.freqs.dtype == dt and self.freqs.is_contiguous() and self.freqs.shape[1] == DH
+        self.device = device
+        self.graph = None
+        self._ready = True
+
+    # ---------------------------------------------------------------- the step, as C-ABI calls
+    def _gemv(self, lib, stream, lin, a, out, prologue=PRO_NONE, norm=None, resid=None, nxt=None):
+        k2, n = lin.weight.shape
+        if nxt is not None and self.hints:   # experimental L2 prefetch of the NEXT linear's weights (CGQ_PF_MB)
+            _lib.check(lib.cgq_prefetch_next_w4(nxt.weight.data_ptr(), nxt.weight_scale.data_ptr(),
+                                                nxt.weight.shape[1], nxt.weight.shape[0] * 2))
+        bias = lin.bias if getattr(lin, "bias", None) is not None else None
+        _lib.check(lib.cgq_w4a16_gemv_fused(
+            a.data_ptr(), lin.weight.data_ptr(), lin.weight_scale.data_ptr(),
+            None if bias is None else bias.data_ptr(), None if resid is None else resid.data_ptr(),
+            out.data_ptr(), n, 2 * k2, 32, self.code, prologue,
+            None if norm is None else norm.weight.data_ptr(), float(norm.eps) if norm is not None else 0.0,
+            stream))
+
+    def _launch_step(self):
+        lib = _lib.load()
+        cfg, m = self.cfg, self.model
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        emb = m.word_embedding
+        _lib.check(lib.cgq_decode_begin_w4(
+            self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
+            emb.weight.shape[0] * 2, emb.weight.shape[1], 32, self.code, self.state.data_ptr(), stream))
+        firsts = [layer.attn.qkv_proj for layer in m.layers][1:] + [m.lm_head]
+        for layer, (kc, vc), nxt in zip(m.layers, self.kv, firsts):
+            self._gemv(lib, stream, layer.attn.qkv_proj, self.x, self.qkv, PRO_RMSNORM, layer.attn_ln,
+                       nxt=layer.attn.o_proj)
+            _lib.check(lib.cgq_decode_attention(
+                self.qkv.data_ptr(), self.freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.ao.data_ptr(),
+                self.state.data_ptr(), cfg.num_attention_heads, cfg.num_multi_query_groups,
+                cfg.head_hidden_size, self.max_len, self.code, stream))
+            self._gemv(lib, stream, layer.attn.o_proj, self.ao, self.x, resid=self.x, nxt=layer.ffn.w_in)
+            self._gemv(lib, stream, layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln, nxt=layer.ffn.w_out)
+            self._gemv(lib, stream, layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x, nxt=nxt)
+        self._gemv(lib, stream, m.lm_head, self.x, self.logits, PRO_RMSNORM, m.final_ln,
+                   nxt=m.layers[0].attn.qkv_proj)     # the next token's first linear
+
+    def launches_per_step(self) -> int:
+        return 5 * self.cfg.num_layers + 2
+
+    def _capture(self):
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        state0 = self.state.clone()
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.cuda.device(dev):
+            self._launch_step()                       # warm-up: tensor maps, function attributes
+            side.synchronize()
+            self.state.copy_(state0)                  # the warm-up step consumed a position; take it back
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._launch_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.state.copy_(state0)
+
+    # ---------------------------------------------------------------- model(...) as the decoder calls it
+    @torch.no_grad()
+    def __call__(self, input_ids: Tensor = None, past_key_values=None, **kwargs):
+        if kwargs or input_ids is None:
+            return self.model(input_ids=input_ids, past_key_values=past_key_values, **kwargs)
+        fresh = past_key_values is None or not isinstance(past_key_values, _FusedCache)
+        if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
+            loss, logits, kv = self.model(input_ids=input_ids,
+                                          past_key_values=None if fresh else self._export_kv())
+            self._import_kv(kv, input_ids.device)
+            return loss, logits, _FusedCache(self)
+        if self._eager_kv is not None or self.n_valid + 1 > self.max_len:
+            if self._eager_kv is None:
+                self._eager_kv = self._export_kv()
+            loss, logits, self._eager_kv = self.model(input_ids=input_ids, past_key_values=self._eager_kv)
+            return loss, logits, past_key_values
+        self.ids.copy_(input_ids, non_blocking=True)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        self.n_valid += 1
+        return None, self.logits, past_key_values
+
+    # ---------------------------------------------------------------- cache import / export
+    def _import_kv(self, kv, device):
+        n = kv[0][0].shape[1]
+        self._eager_kv = None
+        self.n_valid = n
+        if n + 1 > self.max_len or kv[0][0].shape[0] != 1:
+            self._eager_kv = kv
+            return
+        if not self._ready or self.device != device:
+            self._setup(device)
+        for (ks, vs), (k, v) in zip(self.kv, kv):
+            ks[:, :n].copy_(k)
+            vs[:, :n].copy_(v)
+        self.state.copy_(torch.tensor([n, n], dtype=torch.int32), non_blocking=False)
+
+    def _export_kv(self):
+        n = self.n_valid
+        return tuple((k[:, :n].clone(), v[:, :n].clone()) for k, v in self.kv)
+
+
+def accelerate(model: torch.nn.Module, max_len: int = 1024):
+    """The fastest decode wrapper this repo has for `model`: the fused step for the int4g32 model,
+    the CUDA-graphed reference forward (graph_decode.GraphDecodeModel) for everything else."""
+    try:
+        return FusedDecodeModel(model, max_len=max_len)
+    except TypeError:
+        from .graph_decode import GraphDecodeModel
+
+        return GraphDecodeModel(model, max_len=max_len)

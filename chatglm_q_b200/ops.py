@@ -205,3 +205,56 @@ def embedding_s8(ids: Tensor, weight: Tensor, weight_scale: Tensor) -> Tensor:
             flat.data_ptr(), flat.numel(), weight.data_ptr(), weight_scale.data_ptr(), out.data_ptr(),
             V, D, code, torch.cuda.current_stream().cuda_stream))
     return out.reshape(*ids.shape, D)
+
+
+# ---------------------------------------------------------------------- fused decode-step pieces
+def gemv_fused_s4(a: Tensor, b: Tensor, b_scale: Tensor, bias: Tensor = None, resid: Tensor = None,
+                  prologue: int = _lib.PRO_NONE, norm_weight: Tensor = None, eps: float = 0.0,
+                  out: Tensor = None) -> Tensor:
+    """One-row int4 linear of the fused decode step (cgq_w4a16_gemv_fused, include/cgq.h):
+    out[N] = (resid +) round(prologue(a) · dequant(b, b_scale)) (+ bias).
+
+    prologue PRO_RMSNORM: a [K] is the residual stream, normalised as RMSNorm.forward does (model.py:68-73);
+    PRO_SILU_GATE: a [2K] is w_in's output, a' = silu(a[:K]) * a[K:] (model.py:200-201).
+    `out` may alias `resid` (the in-place residual update of the step)."""
+    K, N = b.shape[0] * 2, b.shape[1]
+    code = _dtype_code(a)
+    assert a.dim() == 1 and a.is_contiguous() and a.numel() == (2 * K if prologue == _lib.PRO_SILU_GATE else K)
+    assert b.dtype == torch.uint8 and b.is_contiguous() and b_scale.is_contiguous()
+    assert b_scale.shape == (K // 32, N) and b_scale.dtype == a.dtype
+    for t in (bias, resid):
+        assert t is None or (t.shape == (N,) and t.dtype == a.dtype and t.is_contiguous())
+    if prologue == _lib.PRO_RMSNORM:
+        assert norm_weight is not None and norm_weight.shape == (K,) and norm_weight.dtype == a.dtype
+    if out is None:
+        out = torch.empty(N, device=a.device, dtype=a.dtype)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().cgq_w4a16_gemv_fused(
+            a.data_ptr(), b.data_ptr(), b_scale.data_ptr(), _ptr(bias), _ptr(resid), out.data_ptr(), N, K, 32,
+            code, prologue, _ptr(norm_weight), float(eps), torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def decode_attention(qkv: Tensor, freqs: Tensor, k_cache: Tensor, v_cache: Tensor, state: Tensor,
+                     n_head: int, n_groups: int, d_head: int) -> Tensor:
+    """ChatGLM2Attention.forward between qkv_proj and o_proj for one new token (cgq_decode_attention):
+    RoPE with row state[1]+1 of `freqs`, append k/v at slot state[1] of the [max_len, n_groups, d_head]
+    caches (in place), attention over slots 0..state[1].  Returns [n_head * d_head]."""
+    code = _dtype_code(qkv)
+    max_len = k_cache.shape[0]
+    assert qkv.numel() == d_head * (n_head + 2 * n_groups) and qkv.is_contiguous()
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and k_cache.numel() == max_len * n_groups * d_head
+    assert state.dtype == torch.int32 and state.numel() >= 2 and freqs.is_contiguous() and freqs.dtype == qkv.dtype
+    out = torch.empty(n_head * d_head, device=qkv.device, dtype=qkv.dtype)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().cgq_decode_attention(
+            qkv.data_ptr(), freqs.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+            state.data_ptr(), n_head, n_groups, d_head, max_len, code, torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def prefetch_next_s4(b: Tensor, b_scale: Tensor) -> None:
+    """One-shot hint (cgq_prefetch_next_w4): the NEXT int4 decode launch of this thread also streams the
+    leading part of THIS weight — the one the launch after it will read — from HBM into L2."""
+    assert b.dtype == torch.uint8 and b.is_contiguous() and b_scale.is_contiguous() and b.get_device() >= 0
+    _lib.check(_lib.load().cgq_prefetch_next_w4(b.data_ptr(), b_scale.data_ptr(), b.shape[1], b.shape[0] * 2))

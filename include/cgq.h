@@ -127,6 +127,62 @@ int cgq_w8_embedding(const int64_t* ids, int n_ids, const int8_t* Wq /*[V, D]*/,
                      const void* scale /*[D]*/, void* out, int V, int D, int dtype, void* stream);
 
 /*
+ * ---- Fused batch-1 decode step --------------------------------------
+ * What ChatGLM2Model.forward (chatglm_q/model.py:329-392) does for ONE new token against a KV
+ * cache, as a chain of launches that a caller captures into one CUDA graph.  Every launch carries
+ * the programmatic-dependent-launch attribute: the next dequant-matmul streams its weights while
+ * the current kernel still runs.  All three calls are asynchronous and allocation-free.
+ *
+ * cgq_w4a16_gemv_fused: C[N] = (resid[N] +) round(prologue(A) · dequant(Wq, scale)) (+ bias), M == 1.
+ *   prologue CGQ_PRO_NONE      a = A[0..K)
+ *            CGQ_PRO_RMSNORM   a = round(round(A * rsqrt(mean(A^2) + eps)) * norm_w)
+ *                              — RMSNorm.forward feeding the linear (model.py:62-73, 231, 244, 381)
+ *            CGQ_PRO_SILU_GATE a[k] = round(round(silu(A[k])) * A[K + k]), A has 2K elements
+ *                              — GatedFeedForward.forward between w_in and w_out (model.py:200-201)
+ *   resid (nullable) is the residual stream: `x = x + h` (model.py:243, 246); C may alias resid.
+ */
+#define CGQ_PRO_NONE 0
+#define CGQ_PRO_RMSNORM 1
+#define CGQ_PRO_SILU_GATE 2
+int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void* scale, const void* bias,
+                         const void* resid, void* C, int N, int K, int group, int dtype,
+                         int prologue, const void* norm_w, float eps, void* stream);
+
+/*
+ * EXPERIMENTAL one-shot hint (no reference counterpart): the NEXT int4 decode launch (M <= 8) issued by
+ * the calling thread also streams the leading part (at most CGQ_PF_MB MiB) of THIS weight — the one
+ * the launch after it will read — from HBM into L2 with `cp.async.bulk.prefetch.L2`, in the order
+ * that launch will consume it, so that HBM keeps streaming across the dependency bubble between two
+ * launches.  Measured on B200 it is a net loss (the decode kernel is issue-bound on the SM, not
+ * HBM-bound, and the prefetches queue in front of its own TMA loads), so it is DISABLED
+ * unless the environment sets CGQ_PF_MB > 0; the call is then a no-op.  Results are never affected.
+ * Wq == NULL cancels.
+ */
+int cgq_prefetch_next_w4(const uint8_t* Wq, const void* scale, int N, int K);
+
+/*
+ * First launch of a decode step: x[D] = int4 QEmbedding row of token ids[0]
+ * (int4/qlinear.py:122-130) and the device-side position bookkeeping:
+ *   state[1] = state[0]  (tokens in the KV cache before this step, used by cgq_decode_attention)
+ *   state[0] += 1
+ * The host sets state[0] once after prefill; afterwards the step is a static CUDA graph.
+ */
+int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq /*[V/2, D]*/, const void* scale,
+                        void* x, int V, int D, int group, int dtype, int* state, void* stream);
+
+/*
+ * ChatGLM2Attention.forward between qkv_proj and o_proj for one new token (model.py:140-174):
+ * RoPE of q and k with row (state[1] + 1) of `freqs` (the model's freqs_cis_cache, [max_pos, d_head];
+ * position ids are 1-based, model.py:296-297), append k / v to the caches at slot state[1]
+ * (layout [max_len, n_groups, d_head], the reference's past_key_values layout without the batch and
+ * broadcast axes), multi-query attention over slots 0..state[1], output [n_head * d_head].
+ * d_head must be 64 or 128; state[1] must be < max_len (the launch is a no-op otherwise).
+ */
+int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void* vcache, void* out,
+                         const int* state, int n_head, int n_groups, int d_head, int max_len,
+                         int dtype, void* stream);
+
+/*
  * Profiling aid (no reference counterpart): the NEXT decode-kernel launch issued by the calling
  * thread writes a per-CTA timeline (8 x uint64 %globaltimer stamps per CTA, first 1024 CTAs:
  * entry, producer start, consumer dependency wait passed, first data, loop end, exit,

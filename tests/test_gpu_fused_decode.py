@@ -1,0 +1,249 @@
+"""GPU suite (-m gpu) of the fused batch-1 decode step: the fused int4 linear
+(RMSNorm / SiLU-gate prologue, residual epilogue), the RoPE + KV + attention kernel and the whole step
+behind the model call signature — against oracle/decode_oracle.py on seeded inputs, against the golden
+fixture made by the REAL reference model (tests/golden/decode_tiny.npz) and, when the pip-installed
+reference is present (baseline/_ref), against the unmodified reference model running on the same GPU.
+"""
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_oracle as dec
+from oracle import qmatmul_oracle as orc
+from util import assert_parity, from_torch, load_decode_golden, make_int4_case, rtol_for, to_torch
+
+pytestmark = pytest.mark.gpu
+
+from chatglm_q_b200 import ops  # noqa: E402
+from chatglm_q_b200._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE  # noqa: E402
+from chatglm_q_b200.fused_decode import FusedDecodeModel, _FusedCache, accelerate  # noqa: E402
+
+DEV = "cuda"
+
+
+def u8(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+# ------------------------------------------------------------------ fused linear
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("k,n", [(4096, 4608), (4096, 27392), (512, 768), (4096 + 2048, 256), (1056, 144)])
+def test_gemv_fused_rmsnorm_bias(dtype, k, n):
+    a, bq, s = make_int4_case(31, 1, k, n, "Q", dtype)
+    rng = np.random.default_rng(5)
+    x = orc.round_to(a[0] * 3.0, dtype)
+    nw = orc.round_to(1.0 + 0.2 * rng.standard_normal(k), dtype)
+    bias = orc.round_to(rng.standard_normal(n) * 0.05, dtype)
+    got = ops.gemv_fused_s4(to_torch(x, dtype), u8(bq), to_torch(s, dtype), bias=to_torch(bias, dtype),
+                            prologue=PRO_RMSNORM, norm_weight=to_torch(nw, dtype), eps=1e-5)
+    want = orc.qmatmul_int4(dec.rmsnorm(x, nw, 1e-5, dtype)[None], bq, s, bias, dtype)[0]
+    assert_parity(from_torch(got), want, f"rmsnorm+linear {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+    # plain prologue == the module-level op on the same row
+    plain = ops.gemv_fused_s4(to_torch(x, dtype), u8(bq), to_torch(s, dtype), bias=to_torch(bias, dtype))
+    mod = ops.dynamic_quant_matmul_s4(to_torch(x, dtype)[None], u8(bq), to_torch(s, dtype), bias=to_torch(bias, dtype))
+    assert torch.equal(plain, mod[0])
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("k,n", [(13696, 4096), (1024, 512), (384, 256)])
+def test_gemv_fused_silu_gate_residual(dtype, k, n):
+    _, bq, s = make_int4_case(32, 1, k, n, "Q", dtype)
+    rng = np.random.default_rng(6)
+    u = orc.round_to(rng.standard_normal(2 * k) * 1.5, dtype)
+    resid = orc.round_to(rng.standard_normal(n), dtype)
+    x = to_torch(resid, dtype)
+    got = ops.gemv_fused_s4(to_torch(u, dtype), u8(bq), to_torch(s, dtype), resid=x, prologue=PRO_SILU_GATE, out=x)
+    assert got.data_ptr() == x.data_ptr()      # in-place residual update, as the step uses it
+    d = orc.qmatmul_int4(dec.silu_gate(u, dtype)[None], bq, s, None, dtype)[0]
+    want = orc.round_to(resid + d, dtype)
+    assert_parity(from_torch(got), want, f"silu-gate+linear+resid {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+
+
+def test_gemv_fused_prologue_pieces_bit_exact():
+    """With a unit weight (one column per k, nibble 9 = +1, scale 1) the linear returns its own input row, so
+    the fused RMSNorm / SiLU-gate values themselves can be compared with the oracle's.  bfloat16 takes the
+    exact (q - 8) dequant, so the row passes through unchanged; what may differ is the device's rsqrt / exp
+    against numpy's in the last fp32 bit (two roundings => at most 2 bf16 ulps, and rarely)."""
+    k, dt = 256, "bfloat16"
+    rng = np.random.default_rng(9)
+    x = orc.round_to(rng.standard_normal(k) * 2.0, dt)
+    nw = orc.round_to(1.0 + 0.3 * rng.standard_normal(k), dt)
+    q = np.full((k, k), 8, dtype=np.uint8)
+    q[np.arange(k), np.arange(k)] = 9
+    bq = (q[0::2] | (q[1::2] << 4)).astype(np.uint8)
+    s = np.ones((k // 32, k), dtype=np.float32)
+    ident = ops.gemv_fused_s4(to_torch(x, dt), u8(bq), to_torch(s, dt))
+    assert np.array_equal(from_torch(ident), x)
+    got = ops.gemv_fused_s4(to_torch(x, dt), u8(bq), to_torch(s, dt), prologue=PRO_RMSNORM,
+                            norm_weight=to_torch(nw, dt), eps=1e-5)
+    want = dec.rmsnorm(x, nw, 1e-5, dt)
+    diff = np.abs(from_torch(got) - want)
+    assert (diff <= np.abs(want) * 2.0 ** -6 + 1e-7).all() and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())
+    u = orc.round_to(rng.standard_normal(2 * k) * 2.0, dt)
+    got = ops.gemv_fused_s4(to_torch(u, dt), u8(bq), to_torch(s, dt), prologue=PRO_SILU_GATE)
+    want = dec.silu_gate(u, dt)
+    diff = np.abs(from_torch(got) - want)
+    assert (diff <= np.abs(want) * 2.0 ** -6 + 1e-7).all() and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("d_head,n_head,n_groups,n_past", [(128, 32, 2, 0), (128, 32, 2, 1), (128, 32, 2, 159),
+                                                          (128, 32, 2, 700), (64, 8, 2, 37), (64, 4, 4, 5)])
+def test_decode_attention_vs_oracle(dtype, d_head, n_head, n_groups, n_past):
+    rng = np.random.default_rng(100 + n_past)
+    max_len = max(n_past + 3, 16)
+    qkv = orc.round_to(rng.standard_normal(d_head * (n_head + 2 * n_groups)), dtype)
+    kc = orc.round_to(rng.standard_normal((max_len, n_groups, d_head)), dtype)
+    vc = orc.round_to(rng.standard_normal((max_len, n_groups, d_head)), dtype)
+    pos = np.arange(max_len + 2, dtype=np.float64)[:, None] * (1.0 / 10000 ** (np.arange(0, d_head // 2, 2) / (d_head // 2)))
+    table = np.concatenate([np.stack([np.cos(pos), np.sin(pos)], -1), np.stack([np.ones_like(pos), np.zeros_like(pos)], -1)],
+                           axis=-2).reshape(max_len + 2, d_head)
+    table = orc.round_to(table.astype(np.float32), dtype)
+    state = torch.tensor([n_past + 1, n_past], dtype=torch.int32, device=DEV)
+    kct, vct = to_torch(kc, dtype), to_torch(vc, dtype)
+    got = ops.decode_attention(to_torch(qkv, dtype), to_torch(table, dtype), kct, vct, state, n_head, n_groups, d_head)
+    want, k_new, v_new = dec.attention_decode(qkv, table[n_past + 1], kc[:n_past], vc[:n_past], n_head, n_groups,
+                                              d_head, dtype)
+    assert_parity(from_torch(got), want, f"attention {dtype} d={d_head} L={n_past}", rtol=rtol_for(dtype))
+    # the new cache rows are the roped key / raw value (one fp32 product-sum rounded once: <= 1 ulp apart)
+    assert_parity(from_torch(kct[n_past]), k_new, "k cache row", rtol=rtol_for(dtype))
+    assert np.array_equal(from_torch(vct[n_past]), v_new)
+    assert np.array_equal(from_torch(kct[:n_past]), kc[:n_past]) and np.array_equal(from_torch(vct[n_past + 1:]), vc[n_past + 1:])
+
+
+# ------------------------------------------------------------------ the whole step
+def _lin(w, s, b=None):
+    m = SimpleNamespace(weight=u8(w), weight_scale=to_torch(s, "float16"), bias=None if b is None else to_torch(b, "float16"))
+    return m
+
+
+def _duck_model(w, cfg):
+    """A stand-in with the attribute layout of chatglm_q.model.ChatGLM2Model holding the golden weights."""
+    layers = []
+    for i in range(cfg["n_layers"]):
+        p = f"l{i}_"
+        layers.append(SimpleNamespace(
+            attn_ln=SimpleNamespace(weight=to_torch(w[p + "attn_ln"], "float16"), eps=cfg["eps"]),
+            ffn_ln=SimpleNamespace(weight=to_torch(w[p + "ffn_ln"], "float16"), eps=cfg["eps"]),
+            attn=SimpleNamespace(qkv_proj=_lin(w[p + "qkv_w"], w[p + "qkv_s"], w[p + "qkv_b"]),
+                                 o_proj=_lin(w[p + "o_w"], w[p + "o_s"])),
+            ffn=SimpleNamespace(w_in=_lin(w[p + "win_w"], w[p + "win_s"]), w_out=_lin(w[p + "wout_w"], w[p + "wout_s"]))))
+    config = SimpleNamespace(hidden_size=cfg["hidden"], inner_hidden_size=cfg["inner"], head_hidden_size=cfg["d_head"],
+                             num_multi_query_groups=cfg["n_groups"], num_attention_heads=cfg["n_head"],
+                             num_layers=cfg["n_layers"], vocab_size=cfg["vocab"], max_sequence_length=cfg["max_seq"])
+    return SimpleNamespace(config=config, layers=layers,
+                           final_ln=SimpleNamespace(weight=to_torch(w["final_ln"], "float16"), eps=cfg["eps"]),
+                           lm_head=_lin(w["lm_w"], w["lm_s"]),
+                           word_embedding=SimpleNamespace(weight=u8(w["emb_w"]), weight_scale=to_torch(w["emb_s"], "float16")),
+                           freqs_cis_cache=to_torch(w["freqs"], "float16"))
+
+
+def test_fused_step_matches_reference_golden():
+    """Weights, prefill KV and greedy tokens of the REAL reference model (CPU fp16 fixture): the fused CUDA step
+    must reproduce its logits within the parity bar and pick the same tokens; also against the numpy oracle."""
+    w, cfg, fx = load_decode_golden()
+    model = _duck_model(w, cfg)
+    fused = FusedDecodeModel(model, max_len=32)
+    n0 = len(fx["prompt"])
+    kv = tuple((to_torch(fx[f"prefill_k{i}"], "float16").reshape(1, n0, cfg["n_groups"], 1, cfg["d_head"]),
+                to_torch(fx[f"prefill_v{i}"], "float16").reshape(1, n0, cfg["n_groups"], 1, cfg["d_head"]))
+               for i in range(cfg["n_layers"]))
+    fused._import_kv(kv, torch.device("cuda", torch.cuda.current_device()))
+    handle = _FusedCache(fused)
+    okv = [(fx[f"prefill_k{i}"].astype(np.float32), fx[f"prefill_v{i}"].astype(np.float32)) for i in range(cfg["n_layers"])]
+    for step, tok in enumerate(fx["step_tokens"]):
+        _, logits, handle = fused(input_ids=torch.tensor([[int(tok)]], device=DEV), past_key_values=handle)
+        torch.cuda.synchronize()
+        got = from_torch(logits[0, -1])
+        ref = fx["step_logits"][step].astype(np.float32)
+        assert_parity(got, ref, f"fused step {step} vs reference model")
+        top2 = np.sort(ref)[-2:]
+        if top2[1] - top2[0] > 2e-2 * np.abs(ref).max():      # greedy token, unless the reference itself is a near tie
+            assert int(got.argmax()) == int(ref.argmax())
+        want, okv = dec.decode_step(w, int(tok), okv, cfg, "float16")
+        assert_parity(got, want, f"fused step {step} vs oracle")
+    n1 = n0 + len(fx["step_tokens"])
+    for i, (k, v) in enumerate(fused._export_kv()):
+        assert k.shape == (1, n1, cfg["n_groups"], 1, cfg["d_head"])
+        assert_parity(from_torch(k[0, :, :, 0]), fx[f"final_k{i}"].astype(np.float32), f"k cache {i}")
+        assert_parity(from_torch(v[0, :, :, 0]), fx[f"final_v{i}"].astype(np.float32), f"v cache {i}")
+
+
+def _random_ref_model(cfg_kwargs, seed=3):
+    ref = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    from chatglm_q.int4.qlinear import DynamicQuantizeLinear, QEmbedding
+    from chatglm_q.loader import create_quant_int4_model
+    from chatglm_q.model import ChatGLM2Config
+
+    cfg = ChatGLM2Config(**cfg_kwargs)
+    with torch.device(DEV):
+        model = create_quant_int4_model(cfg, 32, torch.float16)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, DynamicQuantizeLinear):
+                k, n = mod.in_features, mod.out_features
+                wq = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+                sc = (torch.rand((k // 32, n), device=DEV, generator=g) * 0.5 + 0.75) / (4.4 * k ** 0.5)
+                b = (torch.randn(n, device=DEV, generator=g) * 0.05).half() if mod.bias is not None else None
+                mod.apply_weights_(wq, sc.half(), b)
+            elif isinstance(mod, QEmbedding):
+                mod.weight.copy_(torch.randint(0, 256, mod.weight.shape, dtype=torch.uint8, device=DEV, generator=g))
+                mod.weight_scale.copy_((torch.rand(mod.weight_scale.shape, device=DEV, generator=g) * 0.2 + 0.05).half())
+        for name, p in model.named_parameters():
+            if name.endswith("ln.weight"):
+                p.copy_((1.0 + 0.2 * torch.randn(p.shape, device=DEV, generator=g)).half())
+    return model.eval()
+
+
+@pytest.mark.parametrize("cfg_kwargs", [
+    dict(hidden_size=512, inner_hidden_size=1024, head_hidden_size=64, num_multi_query_groups=2, num_attention_heads=8,
+         num_layers=3, vocab_size=1024, max_sequence_length=256),
+    dict(hidden_size=4096, inner_hidden_size=13696, head_hidden_size=128, num_multi_query_groups=2,
+         num_attention_heads=32, num_layers=2, vocab_size=65024, max_sequence_length=512),   # ChatGLM2-6B layer shapes
+])
+def test_fused_decode_matches_unmodified_reference_model(cfg_kwargs):
+    """Driven exactly as ChatGLMDecoder.generate does (decoder.py:81-84): prefill, then one token per call.  The
+    fused step must track the UNMODIFIED reference model (same kernels behind its QLinear modules) greedily."""
+    from chatglm_q_b200.install import install, uninstall
+
+    model = _random_ref_model(cfg_kwargs)
+    install("chatglm_q")
+    try:
+        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
+        fused = accelerate(model, max_len=40)
+        assert isinstance(fused, FusedDecodeModel)
+        with torch.no_grad():
+            _, lg_e, kv_e = model(input_ids=prompt)
+            _, lg_f, kv_f = fused(input_ids=prompt, past_key_values=None)
+            assert torch.equal(lg_e, lg_f)
+            tok = lg_e[0, -1].argmax().reshape(1, 1)
+            for step in range(40):     # runs past max_len: the last steps take the exported-cache fallback
+                _, lg_e, kv_e = model(input_ids=tok, past_key_values=kv_e)
+                _, lg_f, kv_f = fused(input_ids=tok, past_key_values=kv_f)
+                a, b = lg_e[0, -1].float(), lg_f[0, -1].float()
+                assert torch.isfinite(b).all()
+                assert_parity(b.cpu().numpy(), a.cpu().numpy(), f"step {step} logits", rtol=2e-2)
+                top2 = a.topk(2).values
+                if (top2[0] - top2[1]).item() > 2e-2 * a.abs().max().item():
+                    assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
+                tok = a.argmax().reshape(1, 1)
+    finally:
+        uninstall("chatglm_q")
+
+
+def test_fused_decode_rejects_unsupported_models():
+    w, cfg, _ = load_decode_golden()
+    model = _duck_model(w, cfg)
+    model.lm_head.weight = model.lm_head.weight.to(torch.int8)       # an int8 model is not this path
+    with pytest.raises(TypeError):
+        FusedDecodeModel(model)

@@ -134,3 +134,23 @@ def test_byte_accounting():
     assert abs(orc.algorithmic_bytes("int4", 1, 27392, 4096) / 1e6 - 63.174) < 1e-3
     assert abs(orc.algorithmic_bytes("int4", 2048, 13696, 4096) / 1e6 - 104.432) < 1e-3
     assert orc.flops(128, 4608, 4096) == 2 * 128 * 4608 * 4096
+
+
+def test_decode_step_oracle_matches_reference_model():
+    """oracle/decode_oracle.py against the REAL reference model (CPU fp16, tests/golden/make_golden_decode.py):
+    prefill KV -> greedy decode steps; logits within the parity bar, same greedy tokens, KV rows equal up to
+    one fp16 ulp (the reference rounds the same fp32 sums)."""
+    from oracle import decode_oracle as dec
+    from util import assert_parity, load_decode_golden
+
+    w, cfg, fx = load_decode_golden()
+    kv = [(fx[f"prefill_k{i}"].astype(np.float32), fx[f"prefill_v{i}"].astype(np.float32))
+          for i in range(cfg["n_layers"])]
+    for step, tok in enumerate(fx["step_tokens"]):
+        logits, kv = dec.decode_step(w, int(tok), kv, cfg, "float16")
+        ref = fx["step_logits"][step].astype(np.float32)
+        assert_parity(logits, ref, f"decode oracle step {step}", rtol=2e-2)
+        assert int(logits.argmax()) == int(ref.argmax())
+    for i in range(cfg["n_layers"]):
+        assert_parity(kv[i][0], fx[f"final_k{i}"].astype(np.float32), f"k cache layer {i}", rtol=2e-2)
+        assert_parity(kv[i][1], fx[f"final_v{i}"].astype(np.float32), f"v cache layer {i}", rtol=2e-2)

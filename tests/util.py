@@ -76,3 +76,22 @@ def make_int8_case(seed: int, m: int, k: int, n: int, kind: str = "Q", dtype: st
         q = rng.integers(-128, 128, size=(n, k), dtype=np.int8)
         s = (rng.standard_normal(n) / 256 / 8).astype(np.float32)  # signed (tests/test_triton_ops.py:12)
     return a, q, orc.round_to(s, dtype)
+
+
+def load_decode_golden():
+    """tests/golden/decode_tiny.npz (reference model, CPU fp16) -> (weights dict, cfg dict, fixture)."""
+    from pathlib import Path
+
+    fx = dict(np.load(Path(__file__).resolve().parent / "golden" / "decode_tiny.npz"))
+    n_head, n_groups, d_head, n_layers, hidden, inner, vocab, max_seq = (int(v) for v in fx["cfg"])
+    cfg = dict(n_head=n_head, n_groups=n_groups, d_head=d_head, n_layers=n_layers, hidden=hidden, inner=inner,
+               vocab=vocab, max_seq=max_seq, eps=float(fx["eps"]))
+    w = {}
+    for k, v in fx.items():
+        if k.endswith(("_w",)):
+            w[k] = v
+        elif k.endswith(("_s", "_b", "_ln")) or k in ("final_ln", "freqs"):
+            w[k] = v.astype(np.float32)
+    for i in range(n_layers):
+        w.setdefault(f"l{i}_qkv_b", None)
+    return w, cfg, fx

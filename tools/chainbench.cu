@@ -4,11 +4,15 @@
 //   chainbench chain  [M] [reps]            ChatGLM2-6B token step: 28 x (qkv,o,w_in,w_out) + lm_head
 //   chainbench single K N [M] [reps]        one shape, weights rotated over > L2 worth of copies
 //   chainbench trace  [M]                   chain once with the in-kernel timeline (cgq_debug_trace)
+//   chainbench step   [ctx] [reps]          FUSED token step (cgq_decode_begin_w4, cgq_w4a16_gemv_fused,
+//                                           cgq_decode_attention): 142 launches, KV context ctx
+//   chainbench steptrace [ctx]              fused step once with the in-kernel timeline of the linears
 //
 // Weights are random bytes (nibbles 1..15), scales ~ 1/(4.4*sqrt(K)) so the chain stays finite.
 // Every timing is CUDA events around `reps` replays of a CUDA graph of the launches.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -90,6 +94,11 @@ static Lin make_lin(int K, int N, bool bias, uint32_t seed) {
 static void* g_ws;
 static size_t g_ws_bytes;
 
+static bool g_hints = false;  // CGQ_PF_MB>0: experimental L2 prefetch hints (cgq_prefetch_next_w4)
+static void hint(const Lin& next) {
+  if (g_hints) CG(cgq_prefetch_next_w4(next.w, next.s, next.N, next.K));
+}
+
 static void run_lin(const Lin& l, const __half* x, __half* y, int M, int lda, cudaStream_t st) {
   CG(cgq_w4a16_gemm(x, lda, l.w, l.s, l.b, y, l.N, M, l.N, l.K, 32, CGQ_DTYPE_F16, g_ws, g_ws_bytes,
                     st));
@@ -112,6 +121,7 @@ static float time_graph(cudaGraphExec_t ge, cudaStream_t st, int reps) {
 
 int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "chain";
+  if (getenv("CGQ_PF_MB") && atoi(getenv("CGQ_PF_MB")) > 0) g_hints = true;
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   g_ws_bytes = cgq_workspace_bytes();
@@ -138,7 +148,10 @@ int main(int argc, char** argv) {
     cudaGraph_t g;
     cudaGraphExec_t ge;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < copies; ++i) run_lin(ls[i], x, y, M, K, st);
+    for (int i = 0; i < copies; ++i) {
+      if (M <= 8) hint(ls[(i + 1) % copies]);
+      run_lin(ls[i], x, y, M, K, st);
+    }
     CK(cudaStreamEndCapture(st, &g));
     CK(cudaGraphInstantiate(&ge, g, 0));
     float ms = time_graph(ge, st, reps);
@@ -146,6 +159,120 @@ int main(int argc, char** argv) {
     double by = (double)ls[0].bytes(M), fl = 2.0 * M * N * (double)K;
     printf("single M=%d K=%d N=%d copies=%d: %.2f us/launch  %.1f GB/s  %.2f TFLOP/s\n", M, K, N,
            copies, us, by / us / 1e3, fl / us / 1e6);
+    return 0;
+  }
+
+  if (!strcmp(mode, "step") || !strcmp(mode, "steptrace")) {
+    const bool tracing = !strcmp(mode, "steptrace");
+    int ctx = argc > 2 ? atoi(argv[2]) : 96;
+    int reps = argc > 3 ? atoi(argv[3]) : 20;
+    const int NH = 32, NG = 2, DH = 128, MAXLEN = ctx + 512;
+    std::vector<Lin> ls;
+    size_t total = 0;
+    for (int l = 0; l < LAYERS; ++l) {
+      ls.push_back(make_lin(H, QKV, true, 1000 + 16 * l));
+      ls.push_back(make_lin(H, H, false, 1001 + 16 * l));
+      ls.push_back(make_lin(H, 2 * INNER, false, 1002 + 16 * l));
+      ls.push_back(make_lin(INNER, H, false, 1003 + 16 * l));
+    }
+    ls.push_back(make_lin(H, VOCAB, false, 9));
+    for (auto& l : ls) total += l.bytes(1);
+    Lin emb = make_lin(VOCAB, H, false, 11);   // [V/2, D] bytes + [V/32, D] scales: the QEmbedding layout
+    __half *x, *qkv, *ao, *u, *logits, *normw, *freqs, *kc, *vc;
+    int64_t* ids;
+    int* state;
+    CK(cudaMalloc(&x, H * 2));
+    CK(cudaMalloc(&qkv, QKV * 2));
+    CK(cudaMalloc(&ao, H * 2));
+    CK(cudaMalloc(&u, 2 * INNER * 2));
+    CK(cudaMalloc(&logits, VOCAB * 2));
+    CK(cudaMalloc(&normw, H * 2));
+    CK(cudaMalloc(&freqs, (size_t)(MAXLEN + 2) * DH * 2));
+    size_t kvb = (size_t)LAYERS * MAXLEN * NG * DH * 2;
+    CK(cudaMalloc(&kc, kvb));
+    CK(cudaMalloc(&vc, kvb));
+    CK(cudaMalloc(&ids, 8));
+    CK(cudaMalloc(&state, 8));
+    fill_h<<<64, 256>>>(normw, H, 3, 0.8f, 1.2f);
+    fill_h<<<64, 256>>>(freqs, (size_t)(MAXLEN + 2) * DH, 4, -1.f, 1.f);
+    fill_h<<<592, 256>>>(kc, kvb / 2, 6, -1.f, 1.f);
+    fill_h<<<592, 256>>>(vc, kvb / 2, 7, -1.f, 1.f);
+    int64_t tok = 1234;
+    CK(cudaMemcpy(ids, &tok, 8, cudaMemcpyHostToDevice));
+    int st0[2] = {ctx, ctx};
+    CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+    uint64_t* trace = nullptr;
+    const int kTraceWords = 8, kTraceCtas = 1024;
+    if (tracing) {
+      CK(cudaMalloc(&trace, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+      CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+    }
+    auto gemv = [&](size_t idx, const __half* a, __half* out, int pro, const __half* resid) {
+      const Lin& l = ls[idx];
+      if (tracing) cgq_debug_trace(trace + idx * kTraceWords * kTraceCtas);
+      hint(ls[(idx + 1) % ls.size()]);
+      CG(cgq_w4a16_gemv_fused(a, l.w, l.s, l.b, resid, out, l.N, l.K, 32, CGQ_DTYPE_F16, pro, normw,
+                              1e-5f, st));
+    };
+    auto step = [&]() {
+      CG(cgq_decode_begin_w4(ids, emb.w, emb.s, x, VOCAB, H, 32, CGQ_DTYPE_F16, state, st));
+      for (int l = 0; l < LAYERS; ++l) {
+        gemv(4 * l + 0, x, qkv, CGQ_PRO_RMSNORM, nullptr);
+        CG(cgq_decode_attention(qkv, freqs, kc + (size_t)l * MAXLEN * NG * DH,
+                                vc + (size_t)l * MAXLEN * NG * DH, ao, state, NH, NG, DH, MAXLEN,
+                                CGQ_DTYPE_F16, st));
+        gemv(4 * l + 1, ao, x, CGQ_PRO_NONE, x);
+        gemv(4 * l + 2, x, u, CGQ_PRO_RMSNORM, nullptr);
+        gemv(4 * l + 3, u, x, CGQ_PRO_SILU_GATE, x);
+      }
+      gemv(4 * LAYERS, x, logits, CGQ_PRO_RMSNORM, nullptr);
+    };
+    step();
+    CK(cudaStreamSynchronize(st));
+    if (tracing) {
+      CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+      step();
+      CK(cudaStreamSynchronize(st));
+      std::vector<uint64_t> h(kTraceWords * kTraceCtas * ls.size());
+      CK(cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost));
+      uint64_t t00 = ~0ull;
+      for (size_t i = 0; i < h.size(); i += kTraceWords)
+        if (h[i]) t00 = std::min(t00, h[i]);
+      const char* names[8] = {"entry", "producer", "depwait", "firstdata", "loopend", "exit", "-", "-"};
+      for (size_t k = 4; k < 13; ++k) {
+        printf("linear %zu (K=%d N=%d):\n", k, ls[k].K, ls[k].N);
+        for (int w = 0; w < 6; ++w) {
+          uint64_t mn = ~0ull, mx = 0;
+          double sum = 0;
+          int cnt = 0;
+          for (int c = 0; c < kTraceCtas; ++c) {
+            uint64_t v = h[(k * kTraceCtas + c) * kTraceWords + w];
+            if (!v) continue;
+            mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)(v - t00); ++cnt;
+          }
+          if (cnt)
+            printf("  %-10s n=%4d  min %8.2f  avg %8.2f  max %8.2f us\n", names[w], cnt,
+                   (mn - t00) / 1e3, sum / cnt / 1e3, (mx - t00) / 1e3);
+        }
+      }
+      return 0;
+    }
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    step();
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
+    float ms = time_graph(ge, st, reps);
+    std::vector<__half> hl(VOCAB);
+    CK(cudaMemcpy(hl.data(), logits, VOCAB * 2, cudaMemcpyDeviceToHost));
+    double ss = 0;
+    for (int i = 0; i < VOCAB; ++i) ss += (double)__half2float(hl[i]) * __half2float(hl[i]);
+    printf("fused step ctx=%d..%d: %.1f us/token  %.1f tok/s  %.1f GB/s algorithmic linears (%.3f GB)  142 launches  logits rms %.3f\n",
+           ctx, ctx + reps + 3, ms * 1e3, 1e3 / ms, total / (ms * 1e-3) / 1e9, total / 1e9,
+           sqrt(ss / VOCAB));
     return 0;
   }
 
@@ -184,16 +311,21 @@ int main(int argc, char** argv) {
     for (int l = 0; l < LAYERS; ++l) {
       const Lin* p = &ls[4 * l];
       if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 0) * kTraceWords * kTraceCtas);
+      hint(p[1]);
       run_lin(p[0], cur, b0, M, H, st);
       if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 1) * kTraceWords * kTraceCtas);
+      hint(p[2]);
       run_lin(p[1], b0, b1, M, QKV, st);  // attention stand-in: first 4096 columns of qkv
       if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 2) * kTraceWords * kTraceCtas);
+      hint(p[3]);
       run_lin(p[2], b1, b2, M, H, st);
       if (tracing) cgq_debug_trace(trace + (size_t)(4 * l + 3) * kTraceWords * kTraceCtas);
+      hint(p[4]);   // next block's qkv_proj, or lm_head after the last block
       run_lin(p[3], b2, b3, M, 2 * INNER, st);  // silu*gate stand-in: first 13696 columns
       cur = b3;
     }
     if (tracing) cgq_debug_trace(trace + (size_t)(4 * LAYERS) * kTraceWords * kTraceCtas);
+    hint(ls[0]);    // the next token's first linear
     run_lin(ls.back(), cur, logits, M, H, st);
   };
   chain();
