@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(kThreads)
     const uint32_t wa = Wsm + slot * W_BYTES + (16 * warp + g) * KSTAGE;  // row g of this warp
     const uint32_t wb = wa + 8 * KSTAGE;                                   // row g + 8
     const uint32_t arow = Asm + slot * A_BYTES + g * A_STRIDE + (32 * tig) * 2;
+    uint32_t ld_dep = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int chunk = 2 * tig + h;  // 16-byte run: k = 16*chunk .. +15
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kThreads)
         a0 = ptx::lds128(arow + 32 * h);
         a1 = ptx::lds128(arow + 32 * h + 16);
       }
+      ld_dep = qa.x | qb.x | a0.x | a1.x;
       const uint32_t wqa[4] = {qa.x, qa.y, qa.z, qa.w};
       const uint32_t wqb[4] = {qb.x, qb.y, qb.z, qb.w};
       const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -187,7 +189,9 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&empty[slot]);
+    // release the slot only once every load from it has returned (ptx::mbar_arrive_after_loads)
+    if (lane == 0)
+      ptx::mbar_arrive_after_loads(&empty[slot], ld_dep, static_cast<uint32_t>(p.K) >> 31);
     if (++slot == S) {
       slot = 0;
       phase ^= 1;

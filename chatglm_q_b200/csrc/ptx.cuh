@@ -28,6 +28,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Consumer release of a ring slot: arrive on `bar` only AFTER the shared-memory loads that produced `dep`
+// have returned their data.  `mbarrier.arrive` does not wait for the warp's outstanding ld.shared, and
+// the producer answers the release with a TMA write into the same slot: a load still queued in the LSU
+// can then read the NEXT stage's bytes (seen on B200 when the refill hits L2).  Making the barrier
+// ADDRESS depend on the loaded registers forces the scoreboard wait.  `zero` must be a run-time zero the
+// compiler cannot fold (e.g. a sign bit of a positive kernel parameter).
+__device__ __forceinline__ void mbar_arrive_after_loads(uint64_t* bar, uint32_t dep, uint32_t zero) {
+  asm volatile(
+      "{\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "add.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(dep), "r"(zero)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -400,3 +400,26 @@ def test_graph_decode_matches_eager_reference():
                 tok = a.argmax().reshape(1, 1)
     finally:
         uninstall("chatglm_q")
+
+
+# ------------------------------------------------------------------ repeated launches, multi-wave grids
+@pytest.mark.parametrize("n", [65024, 32768])
+def test_decode_kernel_stress(n):
+    """Every M <= 8 of the decode kernel, launched repeatedly on grids larger than one wave of co-resident CTAs
+    (508 / 512 CTAs), must agree with the bit-faithful CUDA-core kernel EVERY time and with itself bit for bit
+    (this caught a variant that was only wrong in some launches, for M >= 5, when CTAs shared an SM)."""
+    k = 4096
+    g = torch.Generator(device=DEV).manual_seed(n)
+    bq = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+    s = (torch.rand((k // 32, n), device=DEV, generator=g) * 0.02 - 0.01).half()
+    for m in (8, 7, 6, 5, 4, 2, 1):
+        a = torch.randn((m, k), device=DEV, generator=g).half()
+        ref = ops.dynamic_quant_matmul_s4(a, bq, s, impl=ops.IMPL_SIMPLE)
+        first = None
+        for rep in range(10):
+            y = ops.dynamic_quant_matmul_s4(a, bq, s)
+            if first is None:
+                first = y
+                assert_parity(from_torch(y), from_torch(ref), f"stress M={m} N={n}")
+            else:
+                assert torch.equal(y, first), f"M={m} N={n}: launch {rep} differs from launch 0"
