@@ -177,14 +177,6 @@ __device__ __forceinline__ uint4 ldnc128(const void* p) {
   return v;
 }
 template <typename T>
-__device__ __forceinline__ float sum8(const uint4& v) {
-  const T* h = reinterpret_cast<const T*>(&v);
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s += DT<T>::to_f(h[j]);
-  return s;
-}
-template <typename T>
 __device__ __forceinline__ float sumsq8(const uint4& v) {
   const T* h = reinterpret_cast<const T*>(&v);
   float s = 0.f;
@@ -258,7 +250,6 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   // M == 1: activation band of this CTA (band_units x 128 k, zero beyond K), staged by the consumers
   const uint32_t off_band = (off_red + C::RED_BYTES + C::xred_bytes(p.Z) + 16u * S + 15u) & ~15u;
   const uint32_t Aband = base + off_band;
-  const uint32_t off_asum = off_band + static_cast<uint32_t>(p.band_units) * KSTAGE * 2;   // fp32 group sums of the band
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Z = p.Z;
@@ -323,21 +314,12 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   } else {
   // =========================== consumers ===========================
   if (kM1) {
-    // ---- stage the activation band (16-byte chunks of 8 k, zero beyond K) with the fused prologue, and
-    //      the fp32 sum of every 32-k group (the -8 offset of the subnormal trick is -8 * sum)
+    // ---- stage the activation band (16-byte chunks of 8 k, zero beyond K) with the fused prologue
     const int tid = threadIdx.x;                 // 0 .. CW*32-1
     const int nchunk = p.K >> 3;                 // valid chunks of the activation row
     const int c_lo = u0 * (KSTAGE / 8), c_hi = u1 * (KSTAGE / 8);
-    float* asum_w = reinterpret_cast<float*>(gen + off_asum);
-    // called by whole warps; a quad of lanes holds the 4 chunks of one group (bounds are multiples of 4)
     auto put = [&](int c, bool inband, const uint4& v) {
       if (inband) ptx::sts128(Aband + (c - c_lo) * 16, v);
-      if (kTrick) {
-        float cs = inband ? sum8<T>(v) : 0.f;
-        cs += __shfl_xor_sync(0xffffffffu, cs, 1);
-        cs += __shfl_xor_sync(0xffffffffu, cs, 2);
-        if (inband && (tid & 3) == 0) asum_w[(c - c_lo) >> 2] = cs;
-      }
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
     if (kPro == PRO_RMSNORM) {
@@ -403,140 +385,18 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   }
   const int g = lane >> 2, tig = lane & 3;
   const uint32_t rt_zero = static_cast<uint32_t>(p.K) >> 31;   // 0 at run time, opaque to the compiler
-  constexpr int NT = 4;            // accumulator registers kept per MMA tile (M > 1 path)
-  float tot[8][kM1 ? 1 : NT];      // M == 1 accumulates per-warp column sums in shared memory instead
-  if (!kM1) {
+  constexpr int NT = kM1 ? 2 : 4;  // accumulator registers kept per MMA tile
+  float tot[8][NT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int i = 0; i < NT; ++i) tot[j][kM1 ? 0 : i] = 0.f;
-  }
+    for (int i = 0; i < NT; ++i) tot[j][i] = 0.f;
 
   int slot = 0, phase = 0;
-  if constexpr (kM1) {
-    // One token row: the 8 MMA columns carry 8 consecutive k-STAGES instead of 8 tokens.  The lanes
-    // whose B-fragment column equals (stage & 7) supply that stage's activations, all others supply
-    // zeros, so D[:, m] accumulates the group sum of stage slot m and the scale/offset epilogue runs
-    // once per 8 stages on accumulators that are all useful (each lane owns slots 2*tig, 2*tig+1).
-    float acc[8][4];
-    uint32_t sc[2][8];   // scales of this lane's 16 columns for its two stage slots
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      sc[0][j] = sc[1][j] = 0u;
-    }
-    const float* asum = reinterpret_cast<const float*>(gen + off_asum);
-    auto do_stage = [&](int it, auto bank_c) {
-      constexpr int BANK = decltype(bank_c)::value;
-      ptx::mbar_wait(&full[slot], phase);
-      if (it == 0 && threadIdx.x == 0) stamp(p, 3);
-      const int s8 = it & 7;
-      const uint32_t wrow = Wsm + slot * W_BYTES + (16 * warp) * BN;
-      const uint32_t srow = Ssm + slot * S_BYTES + warp * (BN * 2) + g * 32;
-      const uint32_t arow = Aband + (it * KSTAGE + 32 * warp + 4 * tig) * 2;
-      const bool mine_b = (g == s8);
-      uint32_t w_dep = 0;
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int r = 8 * b + 2 * tig;
-        const uint4 q = ptx::lds128(wrow + r * BN + ((g ^ (2 * tig)) << 4));
-        const uint4 pp = ptx::lds128(wrow + (r + 1) * BN + ((g ^ (2 * tig + 1)) << 4));
-        w_dep = q.x | pp.x;
-        uint32_t b0 = 0, b1 = 0;
-        if (mine_b) {
-          const uint2 av = ptx::lds64(arow + 32 * b);  // a[k0+4t .. k0+4t+3]
-          b0 = __byte_perm(av.x, av.y, 0x5410);        // (a[+0], a[+2]) <-> low nibbles of rows r, r+1
-          b1 = __byte_perm(av.x, av.y, 0x7632);        // (a[+1], a[+3]) <-> high nibbles
-          if (kTrick) b1 = h2_mul(b1, 0x2C002C00u);    // * 2^-4: high nibble enters as q * 2^-20
-        }
-        const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-        const uint32_t pw[4] = {pp.x, pp.y, pp.z, pp.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t x = qw[j >> 1], y = pw[j >> 1];
-          const uint32_t v0 = (j & 1) ? __byte_perm(x, y, 0x6622) : __byte_perm(x, y, 0x4400);
-          const uint32_t v1 = (j & 1) ? __byte_perm(x, y, 0x7733) : __byte_perm(x, y, 0x5511);
-          const uint32_t a[4] = {Nib<T, kTrick>::lo(v0), Nib<T, kTrick>::lo(v1),
-                                 Nib<T, kTrick>::hi(v0), Nib<T, kTrick>::hi(v1)};
-          ptx::mma_16816(acc[j], a, b0, b1, acc[j], T());
-        }
-      }
-      if (tig == (s8 >> 1)) {
-        const uint4 sv0 = ptx::lds128(srow), sv1 = ptx::lds128(srow + 16);
-        sc[BANK][0] = sv0.x; sc[BANK][1] = sv0.y; sc[BANK][2] = sv0.z; sc[BANK][3] = sv0.w;
-        sc[BANK][4] = sv1.x; sc[BANK][5] = sv1.y; sc[BANK][6] = sv1.z; sc[BANK][7] = sv1.w;
-      }
-      __syncwarp();
-      // released by a lane that took part in every load of the slot (g == 0, tig == s8 >> 1), with the
-      // barrier address depending on the last-loaded registers: see ptx::mbar_arrive_after_loads
-      if (lane == (s8 >> 1))
-        ptx::mbar_arrive_after_loads(&empty[slot], sc[BANK][0] | sc[BANK][4] | w_dep, rt_zero);
-      if (++slot == S) {
-        slot = 0;
-        phase ^= 1;
-      }
-    };
-    // Scale the block's group sums (s0 = first stage of the block), reduce them over the quad (each of the
-    // 4 lanes holds two different stage slots of the same 16 columns) with a reduce-scatter so that lane
-    // tig ends up with columns 16g+4tig..+3, and add those to this warp's column sums in shared memory.
-    const uint32_t my_red = ptx::smem_u32(red) + static_cast<uint32_t>(warp * BN + 16 * g + 4 * tig) * 4u;
-    auto flush = [&](int s0) {
-      float cor0 = 0.f, cor1 = 0.f;
-      if (kTrick) {
-        const int ua = s0 + 2 * tig;
-        if (ua < n_units) cor0 = -8.f * asum[ua * CW + warp];
-        if (ua + 1 < n_units) cor1 = -8.f * asum[(ua + 1) * CW + warp];
-      }
-      float c[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        // columns 2j (MMA row g -> c0,c1) and 2j+1 (MMA row g+8 -> c2,c3); c0/c2 = slot 2tig, c1/c3 = slot 2tig+1
-        union {
-          uint32_t u;
-          T h[2];
-        } e, o;
-        e.u = sc[0][j];
-        o.u = sc[1][j];
-        const float t0 = kTrick ? fmaf(acc[j][0], 16777216.f, cor0) : acc[j][0];
-        const float t1 = kTrick ? fmaf(acc[j][1], 16777216.f, cor1) : acc[j][1];
-        const float t2 = kTrick ? fmaf(acc[j][2], 16777216.f, cor0) : acc[j][2];
-        const float t3 = kTrick ? fmaf(acc[j][3], 16777216.f, cor1) : acc[j][3];
-        c[2 * j] = fmaf(DT<T>::to_f(e.h[0]), t0, DT<T>::to_f(o.h[0]) * t1);
-        c[2 * j + 1] = fmaf(DT<T>::to_f(e.h[1]), t2, DT<T>::to_f(o.h[1]) * t3);
-        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      }
-      const bool hi2 = (tig & 2) != 0, hi1 = (tig & 1) != 0;
-      float h[8], r[4];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float send = hi2 ? c[k] : c[8 + k];
-        const float keep = hi2 ? c[8 + k] : c[k];
-        h[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float send = hi1 ? h[k] : h[4 + k];
-        const float keep = hi1 ? h[4 + k] : h[k];
-        r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-      }
-      float4 cur;
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(cur.x), "=f"(cur.y), "=f"(cur.z), "=f"(cur.w)
-                   : "r"(my_red));
-      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my_red), "f"(cur.x + r[0]),
-                   "f"(cur.y + r[1]), "f"(cur.z + r[2]), "f"(cur.w + r[3])
-                   : "memory");
-    };
-    asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(my_red), "f"(0.f) : "memory");
-    for (int it = 0; it < n_units; it += 2) {
-      do_stage(it, std::integral_constant<int, 0>{});
-      if (it + 1 < n_units) do_stage(it + 1, std::integral_constant<int, 1>{});
-      if ((it & 7) == 6 || it + 2 >= n_units) flush(it & ~7);
-    }
-  } else {
+  {
   // B fragment: lane (g, tig) supplies token g's activations a[k0+4t .. k0+4t+3] of both halves of the
   // warp's 32-k group, read from L2 one stage ahead of use (zeros for g >= M and for k >= K)
-  const bool has_tok = g < p.M;
+  const bool has_tok = kM1 ? (g == 0) : (g < p.M);
   const T* arow = A + static_cast<int64_t>(has_tok ? g : 0) * p.lda + 32 * warp + 4 * tig;
   auto load_a = [&](int it, uint2 (&dst)[2]) {
     const int k0 = (u0 + it) * KSTAGE;
@@ -551,9 +411,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     }
   };
   uint2 a_cur[2], a_nxt[2];
-  load_a(0, a_cur);
+  if (!kM1) load_a(0, a_cur);
   for (int it = 0; it < n_units; ++it) {
-    load_a(it + 1, a_nxt);
+    if (!kM1) load_a(it + 1, a_nxt);
     ptx::mbar_wait(&full[slot], phase);
     if (it == 0 && threadIdx.x == 0) stamp(p, 3);
     const uint32_t wrow = Wsm + slot * W_BYTES + (16 * warp) * BN;
@@ -576,7 +436,12 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       const uint4 q = ptx::lds128(wrow + r * BN + ((g ^ (2 * tig)) << 4));
       const uint4 pp = ptx::lds128(wrow + (r + 1) * BN + ((g ^ (2 * tig + 1)) << 4));
       w_dep = q.x | pp.x;
-      const uint2 av = a_cur[b];                      // a[k0+4t .. k0+4t+3]
+      uint2 av = make_uint2(0u, 0u);                  // a[k0+4t .. k0+4t+3]
+      if (kM1) {
+        if (has_tok) av = ptx::lds64(Aband + (it * KSTAGE + 32 * warp + 4 * tig) * 2 + 32 * b);
+      } else {
+        av = a_cur[b];
+      }
       uint32_t b0 = __byte_perm(av.x, av.y, 0x5410);   // (a[+0], a[+2]) <-> low nibbles of rows r, r+1
       uint32_t b1 = __byte_perm(av.x, av.y, 0x7632);   // (a[+1], a[+3]) <-> high nibbles
       if (kTrick) b1 = h2_mul(b1, 0x2C002C00u);        // * 2^-4: high nibble enters as q * 2^-20
@@ -626,14 +491,19 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       } cv;
       cv.u = sw[j];
       const float sa = DT<T>::to_f(cv.h[0]), sb = DT<T>::to_f(cv.h[1]);
-      {
+      if (kM1) {   // one token: only MMA column 0 carries data
+        const float t0 = kTrick ? fmaf(grp[j][0], 16777216.f, c0) : grp[j][0];
+        const float t2 = kTrick ? fmaf(grp[j][2], 16777216.f, c0) : grp[j][2];
+        tot[j][0] = fmaf(sa, t0, tot[j][0]);
+        tot[j][1] = fmaf(sb, t2, tot[j][1]);
+      } else {
         const float t0 = kTrick ? fmaf(grp[j][0], 16777216.f, c0) : grp[j][0];
         const float t1 = kTrick ? fmaf(grp[j][1], 16777216.f, c1) : grp[j][1];
         const float t2 = kTrick ? fmaf(grp[j][2], 16777216.f, c0) : grp[j][2];
         const float t3 = kTrick ? fmaf(grp[j][3], 16777216.f, c1) : grp[j][3];
-        constexpr int I1 = kM1 ? 0 : 1, I2 = kM1 ? 0 : 2, I3 = kM1 ? 0 : 3;   // (path compiled for M > 1 only)
+        constexpr int I2 = kM1 ? 0 : 2, I3 = kM1 ? 0 : 3;
         tot[j][0] = fmaf(sa, t0, tot[j][0]);
-        tot[j][I1] = fmaf(sa, t1, tot[j][I1]);
+        tot[j][1] = fmaf(sa, t1, tot[j][1]);
         tot[j][I2] = fmaf(sb, t2, tot[j][I2]);
         tot[j][I3] = fmaf(sb, t3, tot[j][I3]);
       }
@@ -642,22 +512,23 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       slot = 0;
       phase ^= 1;
     }
-    a_cur[0] = a_nxt[0];
-    a_cur[1] = a_nxt[1];
+    if (!kM1) {
+      a_cur[0] = a_nxt[0];
+      a_cur[1] = a_nxt[1];
+    }
   }
   }
   if (threadIdx.x == 0) stamp(p, 4);
 
   // ---------------- band sum of this CTA: cross-warp (k-group) reduction through shared memory
-  if constexpr (!kM1) {   // (M == 1: the warps' column sums are in `red` already)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        const int tok = 2 * tig + (i & 1);
-        const int col = 16 * g + 2 * j + (i >> 1);
-        if (tok < p.M) red[(warp * MR + tok) * BN + col] = tot[j][i];
-      }
+    for (int i = 0; i < NT; ++i) {
+      const int tok = kM1 ? 0 : 2 * tig + (i & 1);
+      const int col = 16 * g + 2 * j + (kM1 ? i : (i >> 1));
+      const bool ok = kM1 ? (tig == 0) : (tok < p.M);
+      if (ok) red[(warp * MR + tok) * BN + col] = tot[j][i];
     }
   }
   ptx::named_bar_sync(1, CW * 32);
@@ -755,7 +626,7 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
   using C = Cfg<kM1>;
   const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
                       C::xred_bytes(prm.Z) + 16 * stages + 32 +
-                      (kM1 ? static_cast<size_t>(prm.band_units) * (KSTAGE * 2 + CW * 4) : 0);
+                      (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
   auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro>;
   static size_t configured[64] = {0};
   int dev = 0;
