@@ -79,6 +79,17 @@ def load_peaks() -> dict:
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the decode kernel, from the committed ncu
+    launch list of this same step (profiles/r01_token_summary.json, scripts/gpu_profile.sh); None if absent."""
+    p = ROOT / "profiles" / "r01_token_summary.json"
+    try:
+        d = json.loads(p.read_text())
+        return round(float(d["dram_bytes"]) / int(d["launches"]))
+    except (OSError, KeyError, ValueError, ZeroDivisionError):
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -524,7 +535,8 @@ def run_own_arm(args):
     roofline = {"bound": "hbm", "kernel": "w4_gemv_kernel", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                 "frac_of_8TBps_nominal": round(achieved / 8000.0, 4), "peak_source": peaks["source"],
-                "traffic": None,
+                "traffic": ncu_traffic_per_launch() if world == 1 else None,
+                "algorithmic_bytes_per_launch": round(total_bytes / step.launches),
                 "algorithmic_bytes_per_step": total_bytes, "launches_per_step": step.launches,
                 "avg_launch_us": round(ms_per_step * 1e3 / step.launches, 3),
                 "note": "per rank; includes the inter-kernel gaps of the graph-replayed step (and NCCL at N>1)"}

@@ -30,13 +30,18 @@ __global__ void __launch_bounds__(256)
     decode_begin_w4_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ Wq,
                            const T* __restrict__ scale, T* __restrict__ x, int D, int group,
                            int* __restrict__ state) {
-  ptx::pdl_launch_dependents();
+  // First kernel of the step's graph: everything before it has completed.  The position is published
+  // (written + fenced) BEFORE the dependents are released, so that the attention kernels further down the
+  // programmatic-launch chain may read state[1] ahead of their own griddepcontrol.wait.
   ptx::pdl_wait_prior_grid();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const int cur = state[0];
     state[1] = cur;
     state[0] = cur + 1;
+    __threadfence();
   }
+  __syncthreads();
+  ptx::pdl_launch_dependents();
   const int64_t t = ids[0];
   const uint8_t* wrow = Wq + (t >> 1) * D;
   const T* srow = scale + (t / group) * D;
@@ -60,27 +65,45 @@ constexpr int kAttnThreads = 512;
 constexpr int kAttnWarps = kAttnThreads / 32;
 constexpr int kRowsPerIter = 8;   // cache rows a warp has in flight
 
+// activations written by the previous kernel of the chain are read past L1 (a stale line from an earlier
+// layer's use of the same buffer must never be hit)
+template <typename T>
+__device__ __forceinline__ T ldcg_16(const T* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return *reinterpret_cast<T*>(&v);
+}
 __device__ __forceinline__ int ldcg_i32(const int* p) {
   int v;
   asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 
+// One cache row = 32 lanes x EPL elements.  The load is kept raw (registers) so that many rows can be in
+// flight before the first conversion waits on one of them.
+template <int EPL>
+struct RawRow {
+  uint32_t w[EPL / 2];
+};
+template <typename T, int EPL>
+__device__ __forceinline__ RawRow<EPL> load_raw(const T* row, int lane) {
+  RawRow<EPL> r;
+  if (EPL == 4) {
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[EPL / 2 - 1]) : "l"(row + lane * 4));
+  } else {
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(row + lane * 2));
+  }
+  return r;
+}
+template <typename T, int EPL>
+__device__ __forceinline__ void cvt_row(const RawRow<EPL>& r, float (&f)[EPL]) {
+  const T* h = reinterpret_cast<const T*>(r.w);
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) f[e] = DT<T>::to_f(h[e]);
+}
 template <typename T, int EPL>
 __device__ __forceinline__ void load_row(const T* row, int lane, float (&f)[EPL]) {
-  if (EPL == 4) {
-    uint2 v;
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(row + lane * 4));
-    const T* h = reinterpret_cast<const T*>(&v);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) f[e] = DT<T>::to_f(h[e]);
-  } else {
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(row + lane * 2));
-    const T* h = reinterpret_cast<const T*>(&v);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) f[e] = DT<T>::to_f(h[e]);
-  }
+  cvt_row<T, EPL>(load_raw<T, EPL>(row, lane), f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -95,7 +118,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 template <typename T, int DH>
-__global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const AttnParams p) {
   constexpr int EPL = DH / 32;
   extern __shared__ float sm[];
   float* q_s = sm;                     // rotated, scaled query (T-rounded values)
@@ -110,8 +133,9 @@ __global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnPar
   const int g = h / hpg;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   ptx::pdl_launch_dependents();
-  ptx::pdl_wait_prior_grid();
-
+  // Everything that does not depend on this step's qkv is requested BEFORE the dependency wait, while the
+  // qkv projection is still running: the position (published by decode_begin ahead of its own dependents),
+  // the rotary row and the first block of cached K / V rows (written by earlier steps).
   const int n_past = ldcg_i32(p.state + 1);
   if (n_past >= p.max_len) return;     // window exhausted: the host never launches in this state
   const T* qkv = static_cast<const T*>(p.qkv);
@@ -120,14 +144,36 @@ __global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnPar
   T* vc = static_cast<T*>(p.vcache);
   const size_t row_stride = static_cast<size_t>(p.n_groups) * DH;
   const bool writer = (h % hpg) == 0;
+  // The K and V rows of the FIRST block of cached rows only depend on n_past: request them now, so their
+  // L2 latency overlaps the qkv / rope work below (contexts up to kAttnWarps * kRowsPerIter = 128 rows never
+  // wait on L2 again)
+  const T* kbase = kc + g * DH;
+  const T* vbase = vc + g * DH;
+  RawRow<EPL> k0raw[kRowsPerIter], v0raw[kRowsPerIter];
+#pragma unroll
+  for (int i = 0; i < kRowsPerIter; ++i) {
+    const int l = warp + i * kAttnWarps;
+    if (l < n_past) {
+      k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
+      v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+    }
+  }
+
+  float fc = 1.f, fs = 0.f;
+  if (t < DH) {
+    const int j = t < DH / 2 ? t : t - DH / 2;
+    fc = DT<T>::to_f(fr[2 * j]);
+    fs = DT<T>::to_f(fr[2 * j + 1]);
+  }
+  ptx::pdl_wait_prior_grid();
 
   if (t < DH) {
     // rope of pair j of q (t < DH/2) or k (t >= DH/2)
     const bool is_q = t < DH / 2;
     const int j = is_q ? t : t - DH / 2;
     const T* src = is_q ? qkv + h * DH : qkv + (p.n_head + g) * DH;
-    const float a = DT<T>::to_f(src[2 * j]), b = DT<T>::to_f(src[2 * j + 1]);
-    const float c = DT<T>::to_f(fr[2 * j]), s = DT<T>::to_f(fr[2 * j + 1]);
+    const float a = DT<T>::to_f(ldcg_16(src + 2 * j)), b = DT<T>::to_f(ldcg_16(src + 2 * j + 1));
+    const float c = fc, s = fs;
     const T re = DT<T>::from_f(a * c - b * s);
     const T im = DT<T>::from_f(a * s + b * c);
     if (is_q) {
@@ -144,7 +190,7 @@ __global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnPar
     }
   } else if (t < 2 * DH) {
     const int d = t - DH;
-    const T v = qkv[(p.n_head + p.n_groups + g) * DH + d];
+    const T v = ldcg_16(qkv + (p.n_head + p.n_groups + g) * DH + d);
     v_s[d] = DT<T>::to_f(v);
     if (writer) vc[n_past * row_stride + g * DH + d] = v;
   }
@@ -154,21 +200,23 @@ __global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnPar
   float qr[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) qr[e] = q_s[lane * EPL + e];
-  const T* kbase = kc + g * DH;
   for (int l0 = warp; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
-    float kr[kRowsPerIter][EPL];
+    if (l0 != warp) {   // later blocks: request their rows now (the first block is already in flight)
 #pragma unroll
-    for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = l0 + i * kAttnWarps;
-      if (l < n_past) load_row<T, EPL>(kbase + l * row_stride, lane, kr[i]);
+      for (int i = 0; i < kRowsPerIter; ++i) {
+        const int l = l0 + i * kAttnWarps;
+        if (l < n_past) k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
+      }
     }
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
       const int l = l0 + i * kAttnWarps;
       if (l < n_past) {
+        float kr[EPL];
+        cvt_row<T, EPL>(k0raw[i], kr);
         float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[i][e], d);
+        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
         d = warp_sum(d);
         if (lane == 0) sc[l] = DT<T>::to_f(DT<T>::from_f(d));
       }
@@ -213,21 +261,32 @@ __global__ void __launch_bounds__(kAttnThreads) decode_attn_kernel(const AttnPar
   float acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  const T* vbase = vc + g * DH;
-  for (int l0 = warp; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
-    float vr[kRowsPerIter][EPL];
+#pragma unroll
+  for (int i = 0; i < kRowsPerIter; ++i) {
+    const int l = warp + i * kAttnWarps;
+    if (l < n_past) {
+      const float pl = sc[l];
+      float vr[EPL];
+      cvt_row<T, EPL>(v0raw[i], vr);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
+    }
+  }
+  for (int l0 = warp + kAttnWarps * kRowsPerIter; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
       const int l = l0 + i * kAttnWarps;
-      if (l < n_past) load_row<T, EPL>(vbase + l * row_stride, lane, vr[i]);
+      if (l < n_past) v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
     }
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
       const int l = l0 + i * kAttnWarps;
       if (l < n_past) {
         const float pl = sc[l];
+        float vr[EPL];
+        cvt_row<T, EPL>(v0raw[i], vr);
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[i][e], acc[e]);
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
       }
     }
   }

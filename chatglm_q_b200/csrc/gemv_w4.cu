@@ -212,7 +212,9 @@ __device__ __forceinline__ uint4 silu_gate8(const uint4& h, const uint4& g) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float x = DT<T>::to_f(hh[j]);
-    const T act = DT<T>::from_f(x / (1.f + expf(-x)));
+    // fast exp / divide (a few fp32 ulps from torch's expf + IEEE divide; the result is rounded to T anyway:
+    // every CTA of a k-band recomputes its slice, so the accurate versions cost ~1.5 us per launch)
+    const T act = DT<T>::from_f(__fdividef(x, 1.f + __expf(-x)));
     oh[j] = DT<T>::from_f(DT<T>::to_f(act) * DT<T>::to_f(gh[j]));
   }
   return o;
