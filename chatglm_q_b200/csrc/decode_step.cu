@@ -59,6 +59,7 @@ struct AttnParams {
   void* out;           // [n_head*DH]
   const int* state;
   int n_head, n_groups, max_len;
+  int splits;          // CTAs per head (cluster size): the context is dealt to them in blocks of 16 rows
 };
 
 constexpr int kAttnThreads = 512;
@@ -117,65 +118,73 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// One query row, one head = one CLUSTER of S CTAs (S = p.splits in {1,2,4,8}).  The cached rows are dealt
+// to the CTAs in blocks of kAttnWarps rows (block b -> CTA b % S, row b*16 + warp -> that CTA's warp), so
+// every context length is balanced.  Softmax statistics (max, sum) and the partial outputs are combined
+// through distributed shared memory; the probabilities are rounded to T AFTER the global normalisation,
+// as the reference does.
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const AttnParams p) {
   constexpr int EPL = DH / 32;
+  constexpr int kMaxSplit = 8;
   extern __shared__ float sm[];
-  float* q_s = sm;                     // rotated, scaled query (T-rounded values)
-  float* k_s = q_s + DH;               // rotated new key
-  float* v_s = k_s + DH;               // new value
-  float* red = v_s + DH;               // [kAttnWarps][DH]
-  float* wred = red + kAttnWarps * DH; // [kAttnWarps]
-  float* sc = wred + kAttnWarps;       // [n_past + 1] scores / probabilities
+  float* q_s = sm;                       // rotated, scaled query (T-rounded values)
+  float* k_s = q_s + DH;                 // rotated new key
+  float* v_s = k_s + DH;                 // new value
+  float* red = v_s + DH;                 // [kAttnWarps][DH]
+  float* wred = red + kAttnWarps * DH;   // [kAttnWarps]
+  float* xstat = wred + kAttnWarps;      // [2][kMaxSplit]: (max, sum) of every cluster rank
+  float* xacc = xstat + 2 * kMaxSplit;   // [kMaxSplit][DH]: partial outputs (used on rank 0)
+  float* sc = xacc + kMaxSplit * DH;     // this CTA's scores / probabilities, [own blocks][kAttnWarps] (+ new row)
 
-  const int h = blockIdx.x;
+  const int S = p.splits;
+  const int h = blockIdx.x / S, rank = blockIdx.x - h * S;
   const int hpg = p.n_head / p.n_groups;
   const int g = h / hpg;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   ptx::pdl_launch_dependents();
   // Everything that does not depend on this step's qkv is requested BEFORE the dependency wait, while the
   // qkv projection is still running: the position (published by decode_begin ahead of its own dependents),
-  // the rotary row and the first block of cached K / V rows (written by earlier steps).
+  // the rotary row and the first cached K / V rows of this CTA (written by earlier steps).
   const int n_past = ldcg_i32(p.state + 1);
-  if (n_past >= p.max_len) return;     // window exhausted: the host never launches in this state
+  const bool live = n_past < p.max_len;   // window exhausted: the host never launches in this state
   const T* qkv = static_cast<const T*>(p.qkv);
   const T* fr = static_cast<const T*>(p.freqs) + static_cast<size_t>(n_past + 1) * DH;  // position id = n_past + 1
   T* kc = static_cast<T*>(p.kcache);
   T* vc = static_cast<T*>(p.vcache);
   const size_t row_stride = static_cast<size_t>(p.n_groups) * DH;
-  const bool writer = (h % hpg) == 0;
-  // The K and V rows of the FIRST block of cached rows only depend on n_past: request them now, so their
-  // L2 latency overlaps the qkv / rope work below (contexts up to kAttnWarps * kRowsPerIter = 128 rows never
-  // wait on L2 again)
+  const bool writer = (h % hpg) == 0 && rank == 0;
   const T* kbase = kc + g * DH;
   const T* vbase = vc + g * DH;
+  // i-th block of this CTA -> cached row of this warp
+  auto row_of = [&](int i) { return (i * S + rank) * kAttnWarps + warp; };
+  const int nblk = live ? (n_past + kAttnWarps - 1) / kAttnWarps : 0;      // blocks of cached rows, all CTAs
+  const int my_blk = nblk > rank ? (nblk - rank + S - 1) / S : 0;          // ... dealt to this CTA
   RawRow<EPL> k0raw[kRowsPerIter], v0raw[kRowsPerIter];
 #pragma unroll
   for (int i = 0; i < kRowsPerIter; ++i) {
-    const int l = warp + i * kAttnWarps;
-    if (l < n_past) {
+    const int l = row_of(i);
+    if (i < my_blk && l < n_past) {
       k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
       v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
     }
   }
-
   float fc = 1.f, fs = 0.f;
-  if (t < DH) {
+  if (live && t < DH) {
     const int j = t < DH / 2 ? t : t - DH / 2;
     fc = DT<T>::to_f(fr[2 * j]);
     fs = DT<T>::to_f(fr[2 * j + 1]);
   }
   ptx::pdl_wait_prior_grid();
 
-  if (t < DH) {
+  if (live && t < DH) {
     // rope of pair j of q (t < DH/2) or k (t >= DH/2)
     const bool is_q = t < DH / 2;
     const int j = is_q ? t : t - DH / 2;
     const T* src = is_q ? qkv + h * DH : qkv + (p.n_head + g) * DH;
     const float a = DT<T>::to_f(ldcg_16(src + 2 * j)), b = DT<T>::to_f(ldcg_16(src + 2 * j + 1));
-    const float c = fc, s = fs;
-    const T re = DT<T>::from_f(a * c - b * s);
-    const T im = DT<T>::from_f(a * s + b * c);
+    const T re = DT<T>::from_f(a * fc - b * fs);
+    const T im = DT<T>::from_f(a * fs + b * fc);
     if (is_q) {
       const float inv = 1.0f / sqrtf(static_cast<float>(DH));
       q_s[2 * j] = DT<T>::to_f(DT<T>::from_f(DT<T>::to_f(re) * inv));
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
         kc[n_past * row_stride + g * DH + 2 * j + 1] = im;
       }
     }
-  } else if (t < 2 * DH) {
+  } else if (live && t < 2 * DH) {
     const int d = t - DH;
     const T v = ldcg_16(qkv + (p.n_head + p.n_groups + g) * DH + d);
     v_s[d] = DT<T>::to_f(v);
@@ -196,43 +205,48 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   }
   __syncthreads();
 
-  // ---- scores over the cached rows (one warp per row, kRowsPerIter rows in flight) + the new row
+  // ---- scores of this CTA's cached rows (one warp per row, kRowsPerIter rows in flight) + the new row (rank 0)
   float qr[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) qr[e] = q_s[lane * EPL + e];
-  for (int l0 = warp; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
-    if (l0 != warp) {   // later blocks: request their rows now (the first block is already in flight)
+  const int n_own = my_blk * kAttnWarps;      // score slots of the cached rows; slot n_own = the new row
+  for (int i0 = 0; i0 < my_blk; i0 += kRowsPerIter) {
+    if (i0 != 0) {   // later blocks: request their rows now (the first ones are already in flight)
 #pragma unroll
       for (int i = 0; i < kRowsPerIter; ++i) {
-        const int l = l0 + i * kAttnWarps;
-        if (l < n_past) k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
+        const int l = row_of(i0 + i);
+        if (i0 + i < my_blk && l < n_past) k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
       }
     }
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = l0 + i * kAttnWarps;
-      if (l < n_past) {
-        float kr[EPL];
-        cvt_row<T, EPL>(k0raw[i], kr);
-        float d = 0.f;
+      const int l = row_of(i0 + i);
+      if (i0 + i < my_blk) {
+        float d = -INFINITY;                 // rows past the context (last block only) never win the max
+        if (l < n_past) {
+          float kr[EPL];
+          cvt_row<T, EPL>(k0raw[i], kr);
+          d = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
-        d = warp_sum(d);
-        if (lane == 0) sc[l] = DT<T>::to_f(DT<T>::from_f(d));
+          for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
+          d = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
+        }
+        if (lane == 0) sc[(i0 + i) * kAttnWarps + warp] = d;
       }
     }
   }
-  if (warp == 0) {
+  const bool has_new = live && rank == 0;
+  if (has_new && warp == 0) {
     float d = 0.f;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], k_s[lane * EPL + e], d);
     d = warp_sum(d);
-    if (lane == 0) sc[n_past] = DT<T>::to_f(DT<T>::from_f(d));
+    if (lane == 0) sc[n_own] = DT<T>::to_f(DT<T>::from_f(d));
   }
   __syncthreads();
 
-  // ---- softmax in fp32 over n = n_past + 1 scores, probabilities rounded to T
-  const int n = n_past + 1;
+  // ---- softmax in fp32: local (max, sum), combined over the cluster, probabilities rounded to T
+  const int n = n_own + (has_new ? 1 : 0);
   float mx = -INFINITY;
   for (int l = t; l < n; l += kAttnThreads) mx = fmaxf(mx, sc[l]);
   mx = warp_max(mx);
@@ -243,46 +257,52 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   for (int w = 1; w < kAttnWarps; ++w) mx = fmaxf(mx, wred[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int l = t; l < n; l += kAttnThreads) {
-    const float e = expf(sc[l] - mx);
-    sc[l] = e;
-    sum += e;
-  }
+  for (int l = t; l < n; l += kAttnThreads) sum += expf(sc[l] - mx);   // exp(-inf) = 0 for the padding rows
   sum = warp_sum(sum);
   if (lane == 0) wred[warp] = sum;
   __syncthreads();
   sum = 0.f;
 #pragma unroll
   for (int w = 0; w < kAttnWarps; ++w) sum += wred[w];
-  for (int l = t; l < n; l += kAttnThreads) sc[l] = DT<T>::to_f(DT<T>::from_f(sc[l] / sum));
+  float gmax = mx, gsum = sum;
+  if (S > 1) {
+    if (t < S) {   // publish (max, sum) of this rank in every CTA of the cluster
+      const uint32_t a_m = ptx::mapa_rank(ptx::smem_u32(xstat + rank), t);
+      const uint32_t a_s = ptx::mapa_rank(ptx::smem_u32(xstat + kMaxSplit + rank), t);
+      ptx::st_cluster_f32(a_m, mx);
+      ptx::st_cluster_f32(a_s, sum);
+    }
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    gmax = -INFINITY;
+    for (int r = 0; r < S; ++r) gmax = fmaxf(gmax, xstat[r]);
+    gsum = 0.f;
+    for (int r = 0; r < S; ++r) {
+      const float m_r = xstat[r];
+      if (m_r != -INFINITY) gsum += xstat[kMaxSplit + r] * expf(m_r - gmax);
+    }
+  }
+  for (int l = t; l < n; l += kAttnThreads)
+    sc[l] = DT<T>::to_f(DT<T>::from_f(expf(sc[l] - gmax) / gsum));
   __syncthreads();
 
-  // ---- out = p · V
+  // ---- out = p · V over this CTA's rows
   float acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int i0 = 0; i0 < my_blk; i0 += kRowsPerIter) {
+    if (i0 != 0) {
 #pragma unroll
-  for (int i = 0; i < kRowsPerIter; ++i) {
-    const int l = warp + i * kAttnWarps;
-    if (l < n_past) {
-      const float pl = sc[l];
-      float vr[EPL];
-      cvt_row<T, EPL>(v0raw[i], vr);
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
-    }
-  }
-  for (int l0 = warp + kAttnWarps * kRowsPerIter; l0 < n_past; l0 += kAttnWarps * kRowsPerIter) {
-#pragma unroll
-    for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = l0 + i * kAttnWarps;
-      if (l < n_past) v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+      for (int i = 0; i < kRowsPerIter; ++i) {
+        const int l = row_of(i0 + i);
+        if (i0 + i < my_blk && l < n_past) v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+      }
     }
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = l0 + i * kAttnWarps;
-      if (l < n_past) {
-        const float pl = sc[l];
+      const int l = row_of(i0 + i);
+      if (i0 + i < my_blk && l < n_past) {
+        const float pl = sc[(i0 + i) * kAttnWarps + warp];
         float vr[EPL];
         cvt_row<T, EPL>(v0raw[i], vr);
 #pragma unroll
@@ -290,20 +310,29 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
       }
     }
   }
-  if (warp == 0) {
-    const float pl = sc[n_past];
+  if (has_new && warp == 0) {
+    const float pl = sc[n_own];
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, v_s[lane * EPL + e], acc[e]);
   }
 #pragma unroll
   for (int e = 0; e < EPL; ++e) red[warp * DH + lane * EPL + e] = acc[e];
   __syncthreads();
+  float o = 0.f;
   if (t < DH) {
-    float o = 0.f;
 #pragma unroll
     for (int w = 0; w < kAttnWarps; ++w) o += red[w * DH + t];
-    static_cast<T*>(p.out)[h * DH + t] = DT<T>::from_f(o);
   }
+  if (S > 1) {
+    if (t < DH) ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xacc + rank * DH + t), 0), o);
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    if (rank == 0 && t < DH) {
+      o = 0.f;
+      for (int r = 0; r < S; ++r) o += xacc[r * DH + t];   // rank order: deterministic
+    }
+  }
+  if (live && rank == 0 && t < DH) static_cast<T*>(p.out)[h * DH + t] = DT<T>::from_f(o);
 }
 
 template <typename K, typename... Args>
@@ -323,13 +352,39 @@ int launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args
 }
 
 template <typename T, int DH>
-int launch_attn(const AttnParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (3 * DH + kAttnWarps * DH + kAttnWarps + p.max_len + 1);
+int launch_attn(AttnParams p, cudaStream_t st) {
+  // one CTA per 128 rows of the window (16 warps x 8 rows in flight), powers of two up to the portable
+  // cluster size
+  int S = 1;
+  while (S < 8 && p.max_len > 128 * S) S *= 2;
+  p.splits = S;
+  const int own_rows = ((p.max_len + kAttnWarps - 1) / kAttnWarps + S - 1) / S * kAttnWarps;
+  const size_t smem = sizeof(float) * (3 * DH + kAttnWarps * DH + kAttnWarps + 2 * 8 + 8 * DH + own_rows + 1);
   auto kern = decode_attn_kernel<T, DH>;
   if (smem > 48 * 1024)
     CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-  return launch_pdl(kern, dim3(p.n_head), dim3(kAttnThreads), smem, st, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.n_head * S);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (S > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(S);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  return CGQ_OK;
 }
 
 }  // namespace
@@ -376,7 +431,7 @@ extern "C" int cgq_decode_attention(const void* qkv, const void* freqs, void* kc
     set_error("cgq_decode_attention: null or misaligned pointer");
     return CGQ_ERR_MISALIGNED;
   }
-  AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len};
+  AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len, 1};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CGQ_DTYPE_F16)
     return d_head == 128 ? launch_attn<__half, 128>(p, st) : launch_attn<__half, 64>(p, st);

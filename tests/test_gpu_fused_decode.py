@@ -92,11 +92,14 @@ def test_gemv_fused_prologue_pieces_bit_exact():
 
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
-@pytest.mark.parametrize("d_head,n_head,n_groups,n_past", [(128, 32, 2, 0), (128, 32, 2, 1), (128, 32, 2, 159),
-                                                          (128, 32, 2, 700), (64, 8, 2, 37), (64, 4, 4, 5)])
-def test_decode_attention_vs_oracle(dtype, d_head, n_head, n_groups, n_past):
+@pytest.mark.parametrize("d_head,n_head,n_groups,n_past,window", [
+    (128, 32, 2, 0, 0), (128, 32, 2, 1, 0), (128, 32, 2, 159, 0), (128, 32, 2, 700, 0), (64, 8, 2, 37, 0),
+    (64, 4, 4, 5, 0),
+    # a large KV window deals the context to a cluster of 8 CTAs per head: nearly empty, uneven, full
+    (128, 32, 2, 5, 1024), (128, 32, 2, 130, 1024), (128, 32, 2, 1021, 1024), (64, 8, 2, 300, 512)])
+def test_decode_attention_vs_oracle(dtype, d_head, n_head, n_groups, n_past, window):
     rng = np.random.default_rng(100 + n_past)
-    max_len = max(n_past + 3, 16)
+    max_len = window or max(n_past + 3, 16)
     qkv = orc.round_to(rng.standard_normal(d_head * (n_head + 2 * n_groups)), dtype)
     kc = orc.round_to(rng.standard_normal((max_len, n_groups, d_head)), dtype)
     vc = orc.round_to(rng.standard_normal((max_len, n_groups, d_head)), dtype)
