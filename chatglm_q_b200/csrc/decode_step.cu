@@ -14,8 +14,9 @@
 //   rope      : complex product in fp32, rounded once to T           (torch complex-half mul = fp32 opmath)
 //   q scaling : round_T(q * (1/sqrt(d)))                             (torch divides by a scalar via the reciprocal)
 //   scores    : round_T(fp32 dot)                                    (matmul, :164)
-//   softmax   : fp32 over the scores, rounded to T                   (:168)
-//   output    : round_T(fp32 sum of p_T * v_T)                       (:171)
+//   softmax   : fp32 over the scores (online, per warp); the reference additionally rounds the
+//               probabilities to T (:168) -- ours stay fp32, the more accurate side of the 1e-2 bar
+//   output    : round_T(fp32 sum of p * v_T / fp32 sum of p)         (:171)
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -60,7 +61,16 @@ struct AttnParams {
   const int* state;
   int n_head, n_groups, max_len;
   int splits;          // CTAs per head (cluster size): the context is dealt to them in blocks of 16 rows
+  unsigned long long* trace;  // optional timeline (cgq_debug_trace), 8 words per CTA
 };
+
+__device__ __forceinline__ void attn_stamp(const AttnParams& p, int slot) {
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 
 constexpr int kAttnThreads = 512;
 constexpr int kAttnWarps = kAttnThreads / 32;
@@ -112,17 +122,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 // One query row, one head = one CLUSTER of S CTAs (S = p.splits in {1,2,4,8}).  The cached rows are dealt
 // to the CTAs in blocks of kAttnWarps rows (block b -> CTA b % S, row b*16 + warp -> that CTA's warp), so
-// every context length is balanced.  Softmax statistics (max, sum) and the partial outputs are combined
-// through distributed shared memory; the probabilities are rounded to T AFTER the global normalisation,
-// as the reference does.
+// every context length is balanced.  Each warp keeps an online softmax (running max, sum, un-normalised
+// output) over its rows; warps are combined through shared memory and cluster ranks through distributed
+// shared memory, both in a fixed order (deterministic).
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const AttnParams p) {
   constexpr int EPL = DH / 32;
@@ -132,16 +136,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   float* k_s = q_s + DH;                 // rotated new key
   float* v_s = k_s + DH;                 // new value
   float* red = v_s + DH;                 // [kAttnWarps][DH]
-  float* wred = red + kAttnWarps * DH;   // [kAttnWarps]
-  float* xstat = wred + kAttnWarps;      // [2][kMaxSplit]: (max, sum) of every cluster rank
+  float* wred = red + kAttnWarps * DH;   // [2][kAttnWarps]: running (max, sum) of every warp
+  float* xstat = wred + 2 * kAttnWarps;  // [2][kMaxSplit]: (max, sum) of every cluster rank (used on rank 0)
   float* xacc = xstat + 2 * kMaxSplit;   // [kMaxSplit][DH]: partial outputs (used on rank 0)
-  float* sc = xacc + kMaxSplit * DH;     // this CTA's scores / probabilities, [own blocks][kAttnWarps] (+ new row)
 
   const int S = p.splits;
   const int h = blockIdx.x / S, rank = blockIdx.x - h * S;
   const int hpg = p.n_head / p.n_groups;
   const int g = h / hpg;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  attn_stamp(p, 0);
   ptx::pdl_launch_dependents();
   // Everything that does not depend on this step's qkv is requested BEFORE the dependency wait, while the
   // qkv projection is still running: the position (published by decode_begin ahead of its own dependents),
@@ -175,7 +179,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
     fc = DT<T>::to_f(fr[2 * j]);
     fs = DT<T>::to_f(fr[2 * j + 1]);
   }
+  attn_stamp(p, 1);
   ptx::pdl_wait_prior_grid();
+  attn_stamp(p, 2);
 
   if (live && t < DH) {
     // rope of pair j of q (t < DH/2) or k (t >= DH/2)
@@ -204,135 +210,123 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
     if (writer) vc[n_past * row_stride + g * DH + d] = v;
   }
   __syncthreads();
+  attn_stamp(p, 3);
 
-  // ---- scores of this CTA's cached rows (one warp per row, kRowsPerIter rows in flight) + the new row (rank 0)
+  // ---- every warp runs an online softmax over ITS rows (kRowsPerIter rows in flight): running max m_w,
+  //      running sum s_w and the un-normalised output acc, all in registers -- no score buffer, no block-wide
+  //      pass over the context.  Scores are rounded to T like the reference's matmul output; the
+  //      probabilities stay fp32 (the reference rounds them to T: a deviation of <= 2^-11 per weight).
   float qr[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) qr[e] = q_s[lane * EPL + e];
-  const int n_own = my_blk * kAttnWarps;      // score slots of the cached rows; slot n_own = the new row
+  float m_w = -INFINITY, s_w = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
   for (int i0 = 0; i0 < my_blk; i0 += kRowsPerIter) {
     if (i0 != 0) {   // later blocks: request their rows now (the first ones are already in flight)
 #pragma unroll
       for (int i = 0; i < kRowsPerIter; ++i) {
         const int l = row_of(i0 + i);
-        if (i0 + i < my_blk && l < n_past) k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
+        if (i0 + i < my_blk && l < n_past) {
+          k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
+          v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+        }
       }
     }
+    float sr[kRowsPerIter];
+    float mb = -INFINITY;
 #pragma unroll
     for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = row_of(i0 + i);
-      if (i0 + i < my_blk) {
-        float d = -INFINITY;                 // rows past the context (last block only) never win the max
-        if (l < n_past) {
-          float kr[EPL];
-          cvt_row<T, EPL>(k0raw[i], kr);
-          d = 0.f;
+      sr[i] = -INFINITY;
+      if (i0 + i < my_blk && row_of(i0 + i) < n_past) {   // warp-uniform
+        float kr[EPL];
+        cvt_row<T, EPL>(k0raw[i], kr);
+        float d = 0.f;
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
-          d = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
-        }
-        if (lane == 0) sc[(i0 + i) * kAttnWarps + warp] = d;
+        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
+        sr[i] = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
+        mb = fmaxf(mb, sr[i]);
       }
     }
+    if (mb != -INFINITY) {
+      const float m_new = fmaxf(m_w, mb);
+      const float rescale = expf(m_w - m_new);            // exp(-inf) = 0 on the first batch
+      s_w *= rescale;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] *= rescale;
+#pragma unroll
+      for (int i = 0; i < kRowsPerIter; ++i) {
+        if (sr[i] != -INFINITY) {
+          const float pl = expf(sr[i] - m_new);
+          float vr[EPL];
+          cvt_row<T, EPL>(v0raw[i], vr);
+          s_w += pl;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
+        }
+      }
+      m_w = m_new;
+    }
   }
-  const bool has_new = live && rank == 0;
-  if (has_new && warp == 0) {
+  if (live && rank == 0 && warp == 0) {   // the new token's own key / value
     float d = 0.f;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], k_s[lane * EPL + e], d);
-    d = warp_sum(d);
-    if (lane == 0) sc[n_own] = DT<T>::to_f(DT<T>::from_f(d));
+    const float sn = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
+    const float m_new = fmaxf(m_w, sn);
+    const float rescale = expf(m_w - m_new);
+    const float pl = expf(sn - m_new);
+    s_w = s_w * rescale + pl;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, v_s[lane * EPL + e], acc[e] * rescale);
+    m_w = m_new;
   }
-  __syncthreads();
+  attn_stamp(p, 4);
 
-  // ---- softmax in fp32: local (max, sum), combined over the cluster, probabilities rounded to T
-  const int n = n_own + (has_new ? 1 : 0);
-  float mx = -INFINITY;
-  for (int l = t; l < n; l += kAttnThreads) mx = fmaxf(mx, sc[l]);
-  mx = warp_max(mx);
-  if (lane == 0) wred[warp] = mx;
-  __syncthreads();
-  mx = wred[0];
-#pragma unroll
-  for (int w = 1; w < kAttnWarps; ++w) mx = fmaxf(mx, wred[w]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int l = t; l < n; l += kAttnThreads) sum += expf(sc[l] - mx);   // exp(-inf) = 0 for the padding rows
-  sum = warp_sum(sum);
-  if (lane == 0) wred[warp] = sum;
-  __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int w = 0; w < kAttnWarps; ++w) sum += wred[w];
-  float gmax = mx, gsum = sum;
-  if (S > 1) {
-    if (t < S) {   // publish (max, sum) of this rank in every CTA of the cluster
-      const uint32_t a_m = ptx::mapa_rank(ptx::smem_u32(xstat + rank), t);
-      const uint32_t a_s = ptx::mapa_rank(ptx::smem_u32(xstat + kMaxSplit + rank), t);
-      ptx::st_cluster_f32(a_m, mx);
-      ptx::st_cluster_f32(a_s, sum);
-    }
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-    gmax = -INFINITY;
-    for (int r = 0; r < S; ++r) gmax = fmaxf(gmax, xstat[r]);
-    gsum = 0.f;
-    for (int r = 0; r < S; ++r) {
-      const float m_r = xstat[r];
-      if (m_r != -INFINITY) gsum += xstat[kMaxSplit + r] * expf(m_r - gmax);
-    }
-  }
-  for (int l = t; l < n; l += kAttnThreads)
-    sc[l] = DT<T>::to_f(DT<T>::from_f(expf(sc[l] - gmax) / gsum));
-  __syncthreads();
-
-  // ---- out = p · V over this CTA's rows
-  float acc[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int i0 = 0; i0 < my_blk; i0 += kRowsPerIter) {
-    if (i0 != 0) {
-#pragma unroll
-      for (int i = 0; i < kRowsPerIter; ++i) {
-        const int l = row_of(i0 + i);
-        if (i0 + i < my_blk && l < n_past) v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kRowsPerIter; ++i) {
-      const int l = row_of(i0 + i);
-      if (i0 + i < my_blk && l < n_past) {
-        const float pl = sc[(i0 + i) * kAttnWarps + warp];
-        float vr[EPL];
-        cvt_row<T, EPL>(v0raw[i], vr);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
-      }
-    }
-  }
-  if (has_new && warp == 0) {
-    const float pl = sc[n_own];
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, v_s[lane * EPL + e], acc[e]);
+  // ---- combine the warps (fixed order), then the cluster ranks (fixed order)
+  if (lane == 0) {
+    wred[warp] = m_w;
+    wred[kAttnWarps + warp] = s_w * 0.f + s_w;   // (s_w is identical in all lanes)
   }
 #pragma unroll
   for (int e = 0; e < EPL; ++e) red[warp * DH + lane * EPL + e] = acc[e];
   __syncthreads();
-  float o = 0.f;
+  attn_stamp(p, 5);
+  float M = -INFINITY, o = 0.f, ssum = 0.f;
   if (t < DH) {
 #pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) o += red[w * DH + t];
+    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, wred[w]);
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float m_v = wred[w];
+      const float f = m_v == -INFINITY ? 0.f : expf(m_v - M);
+      o = fmaf(red[w * DH + t], f, o);
+      ssum = fmaf(wred[kAttnWarps + w], f, ssum);
+    }
   }
   if (S > 1) {
     if (t < DH) ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xacc + rank * DH + t), 0), o);
+    if (t == 0) {
+      ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xstat + rank), 0), M);
+      ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xstat + kMaxSplit + rank), 0), ssum);
+    }
     ptx::cluster_arrive_release();
     ptx::cluster_wait_acquire();
     if (rank == 0 && t < DH) {
+      float Mg = -INFINITY;
+      for (int r = 0; r < S; ++r) Mg = fmaxf(Mg, xstat[r]);
       o = 0.f;
-      for (int r = 0; r < S; ++r) o += xacc[r * DH + t];   // rank order: deterministic
+      ssum = 0.f;
+      for (int r = 0; r < S; ++r) {
+        const float m_v = xstat[r];
+        const float f = m_v == -INFINITY ? 0.f : expf(m_v - Mg);
+        o = fmaf(xacc[r * DH + t], f, o);
+        ssum = fmaf(xstat[kMaxSplit + r], f, ssum);
+      }
     }
   }
-  if (live && rank == 0 && t < DH) static_cast<T*>(p.out)[h * DH + t] = DT<T>::from_f(o);
+  if (live && rank == 0 && t < DH) static_cast<T*>(p.out)[h * DH + t] = DT<T>::from_f(o / ssum);
+  attn_stamp(p, 6);
 }
 
 template <typename K, typename... Args>
@@ -353,13 +347,14 @@ int launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args
 
 template <typename T, int DH>
 int launch_attn(AttnParams p, cudaStream_t st) {
-  // one CTA per 128 rows of the window (16 warps x 8 rows in flight), powers of two up to the portable
-  // cluster size
+  // The cluster exchange costs ~1.5 us (DSMEM stores + barrier.cluster), one more 128-row pass of a single
+  // CTA ~0.7 us: a KV window of up to 384 rows stays on one CTA per head, larger windows get one CTA per
+  // 128 rows (16 warps x 8 rows in flight), powers of two up to the portable cluster size.
   int S = 1;
-  while (S < 8 && p.max_len > 128 * S) S *= 2;
+  if (p.max_len > 384)
+    while (S < 8 && p.max_len > 128 * S) S *= 2;
   p.splits = S;
-  const int own_rows = ((p.max_len + kAttnWarps - 1) / kAttnWarps + S - 1) / S * kAttnWarps;
-  const size_t smem = sizeof(float) * (3 * DH + kAttnWarps * DH + kAttnWarps + 2 * 8 + 8 * DH + own_rows + 1);
+  const size_t smem = sizeof(float) * (3 * DH + kAttnWarps * DH + 2 * kAttnWarps + 2 * 8 + 8 * DH);
   auto kern = decode_attn_kernel<T, DH>;
   if (smem > 48 * 1024)
     CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -421,17 +416,14 @@ extern "C" int cgq_decode_attention(const void* qkv, const void* freqs, void* kc
               n_head, n_groups, d_head, max_len);
     return CGQ_ERR_BAD_SHAPE;
   }
-  if (max_len > 32768) {
-    set_error("cgq_decode_attention: max_len %d exceeds the single-CTA score buffer (32768)", max_len);
-    return CGQ_ERR_BAD_SHAPE;
-  }
   if (qkv == nullptr || freqs == nullptr || kcache == nullptr || vcache == nullptr ||
       out == nullptr || state == nullptr ||
       ((reinterpret_cast<uintptr_t>(kcache) | reinterpret_cast<uintptr_t>(vcache)) & 7)) {
     set_error("cgq_decode_attention: null or misaligned pointer");
     return CGQ_ERR_MISALIGNED;
   }
-  AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len, 1};
+  AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len, 1,
+               static_cast<unsigned long long*>(take_trace_buffer())};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CGQ_DTYPE_F16)
     return d_head == 128 ? launch_attn<__half, 128>(p, st) : launch_attn<__half, 64>(p, st);

@@ -176,6 +176,10 @@ int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq /*[V/2, D]*/, cons
  * position ids are 1-based, model.py:296-297), append k / v to the caches at slot state[1]
  * (layout [max_len, n_groups, d_head], the reference's past_key_values layout without the batch and
  * broadcast axes), multi-query attention over slots 0..state[1], output [n_head * d_head].
+ * One CTA per head for max_len <= 384, else a cluster of min(8, ceil(max_len / 128)) CTAs per head.
+ * Online softmax in fp32: the scores are rounded to dtype as the reference's matmul does, the
+ * probabilities are NOT rounded to dtype as the reference's `.type_as(x)` does (the more accurate side
+ * of the parity bar).
  * d_head must be 64 or 128; state[1] must be < max_len (the launch is a no-op otherwise).
  */
 int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void* vcache, void* out,

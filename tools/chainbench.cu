@@ -166,7 +166,7 @@ int main(int argc, char** argv) {
     const bool tracing = !strcmp(mode, "steptrace");
     int ctx = argc > 2 ? atoi(argv[2]) : 96;
     int reps = argc > 3 ? atoi(argv[3]) : 20;
-    const int NH = 32, NG = 2, DH = 128, MAXLEN = ctx + 512;
+    const int NH = 32, NG = 2, DH = 128, MAXLEN = ctx + 64;   // bench.py: prompt + generated + 32
     std::vector<Lin> ls;
     size_t total = 0;
     for (int l = 0; l < LAYERS; ++l) {
@@ -204,9 +204,12 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     uint64_t* trace = nullptr;
     const int kTraceWords = 8, kTraceCtas = 1024;
+    uint64_t* atrace = nullptr;
     if (tracing) {
       CK(cudaMalloc(&trace, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
       CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
+      CK(cudaMalloc(&atrace, sizeof(uint64_t) * kTraceWords * kTraceCtas));
+      CK(cudaMemset(atrace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas));
     }
     auto gemv = [&](size_t idx, const __half* a, __half* out, int pro, const __half* resid) {
       const Lin& l = ls[idx];
@@ -219,6 +222,7 @@ int main(int argc, char** argv) {
       CG(cgq_decode_begin_w4(ids, emb.w, emb.s, x, VOCAB, H, 32, CGQ_DTYPE_F16, state, st));
       for (int l = 0; l < LAYERS; ++l) {
         gemv(4 * l + 0, x, qkv, CGQ_PRO_RMSNORM, nullptr);
+        if (tracing && l == 1) cgq_debug_trace(atrace);
         CG(cgq_decode_attention(qkv, freqs, kc + (size_t)l * MAXLEN * NG * DH,
                                 vc + (size_t)l * MAXLEN * NG * DH, ao, state, NH, NG, DH, MAXLEN,
                                 CGQ_DTYPE_F16, st));
@@ -239,6 +243,23 @@ int main(int argc, char** argv) {
       uint64_t t00 = ~0ull;
       for (size_t i = 0; i < h.size(); i += kTraceWords)
         if (h[i]) t00 = std::min(t00, h[i]);
+      {
+        std::vector<uint64_t> ha(kTraceWords * kTraceCtas);
+        CK(cudaMemcpy(ha.data(), atrace, ha.size() * 8, cudaMemcpyDeviceToHost));
+        const char* an[8] = {"entry", "prewait", "depwait", "rope", "scores", "softmax", "exit", "-"};
+        printf("attention of layer 1:\n");
+        for (int w = 0; w < 7; ++w) {
+          uint64_t mn = ~0ull, mx = 0; double sum = 0; int cnt = 0;
+          for (int c = 0; c < kTraceCtas; ++c) {
+            uint64_t v = ha[c * kTraceWords + w];
+            if (!v) continue;
+            mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)(v - t00); ++cnt;
+          }
+          if (cnt)
+            printf("  %-10s n=%4d  min %8.2f  avg %8.2f  max %8.2f us\n", an[w], cnt, (mn - t00) / 1e3,
+                   sum / cnt / 1e3, (mx - t00) / 1e3);
+        }
+      }
       const char* names[8] = {"entry", "producer", "depwait", "firstdata", "loopend", "exit", "-", "-"};
       for (size_t k = 4; k < 13; ++k) {
         printf("linear %zu (K=%d N=%d):\n", k, ls[k].K, ls[k].N);
