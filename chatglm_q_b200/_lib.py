@@ -24,6 +24,10 @@ SYMBOLS = {
     "cgq_debug_trace": (None, [c_void_p]),
     "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "cgq_program_create": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "cgq_program_run": (c_int, [ctypes.c_uint64, c_void_p]),
+    "cgq_program_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p]),
+    "cgq_program_destroy": (c_int, [ctypes.c_uint64]),
     "cgq_prefetch_next_w4": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "cgq_decode_begin_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p]),
@@ -41,6 +45,13 @@ IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC, IMPL_GEMV_UMMA = 0,
 PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE = 0, 1, 2
 
 _lib = None
+
+
+class LinearOp(ctypes.Structure):
+    """`cgq_linear_op` of include/cgq.h (one batch-1 int4g32 linear of a persistent decode program)."""
+    _fields_ = [("Wq", c_void_p), ("scale", c_void_p), ("bias", c_void_p), ("A", c_void_p), ("C", c_void_p),
+                ("resid", c_void_p), ("norm_w", c_void_p), ("N", c_int), ("K", c_int), ("prologue", c_int),
+                ("eps", c_float)]
 
 
 class CgqError(RuntimeError):

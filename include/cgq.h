@@ -161,6 +161,36 @@ int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void* scale, co
 int cgq_prefetch_next_w4(const uint8_t* Wq, const void* scale, int N, int K);
 
 /*
+ * ---- Persistent decode program: a chain of batch-1 int4g32 linears in ONE launch --------------------
+ * The same linears as cgq_w4a16_gemv_fused (same arithmetic, bit for bit), executed in the given order by
+ * persistent workers: every worker's TMA producer walks the whole chain and keeps its shared-memory ring
+ * full with the weights of whatever comes next, so HBM keeps streaming while the consumer warps wait in the
+ * grid barrier between two dependent linears.  Op i may read what ops < i wrote (A, resid) -- the chain
+ * is executed strictly in order.  All buffers must stay valid and in place while the program exists.
+ *   cgq_program_create  builds the device-side description (tensor maps, work split) once;
+ *   cgq_program_run     = one cudaMemsetAsync + one kernel launch on `stream` (graph-capturable);
+ *   cgq_program_status  synchronises the device and reports the worker count and whether a grid barrier
+ *                       ever timed out (a lost worker: results are then invalid);
+ *   cgq_program_destroy frees it.
+ */
+typedef struct {
+  const uint8_t* Wq;    /* [K/2, N] packed int4 (as cgq_w4a16_gemm) */
+  const void* scale;    /* [K/32, N] dtype */
+  const void* bias;     /* [N] dtype or NULL */
+  const void* A;        /* activation row [K] dtype ([2K] for CGQ_PRO_SILU_GATE) */
+  void* C;              /* output row [N] dtype */
+  const void* resid;    /* [N] dtype or NULL (may alias C) */
+  const void* norm_w;   /* [K] dtype, CGQ_PRO_RMSNORM only */
+  int N, K;
+  int prologue;         /* CGQ_PRO_* */
+  float eps;
+} cgq_linear_op;
+int cgq_program_create(const cgq_linear_op* ops, int n_ops, int dtype, uint64_t* handle);
+int cgq_program_run(uint64_t handle, void* stream);
+int cgq_program_status(uint64_t handle, int* workers, int* failed);
+int cgq_program_destroy(uint64_t handle);
+
+/*
  * First launch of a decode step: x[D] = int4 QEmbedding row of token ids[0]
  * (int4/qlinear.py:122-130) and the device-side position bookkeeping:
  *   state[1] = state[0]  (tokens in the KV cache before this step, used by cgq_decode_attention)

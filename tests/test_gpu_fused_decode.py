@@ -250,3 +250,52 @@ def test_fused_decode_rejects_unsupported_models():
     model.lm_head.weight = model.lm_head.weight.to(torch.int8)       # an int8 model is not this path
     with pytest.raises(TypeError):
         FusedDecodeModel(model)
+
+
+# ------------------------------------------------------------------ persistent decode program (opt-in)
+def test_decode_program_bit_identical_to_per_linear_launches():
+    """A two-block chain (RMSNorm / plain / SiLU-gate prologues, bias, in-place residuals, every band split
+    Z = 8 / 2 / 1) as ONE persistent launch must equal the launch-per-linear results bit for bit, twice in a row."""
+    H, I, V, QKV = 4096, 13696, 65024, 4608
+    g = torch.Generator(device=DEV).manual_seed(5)
+
+    def lin(k, n, bias=False):
+        w = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+        s = ((torch.rand((k // 32, n), device=DEV, generator=g) * 0.5 + 0.75) / (4.4 * k ** 0.5)).half()
+        b = (torch.randn(n, device=DEV, generator=g) * 0.05).half() if bias else None
+        return w, s, b
+
+    blocks = [dict(qkv=lin(H, QKV, True), o=lin(H, H), w_in=lin(H, 2 * I), w_out=lin(I, H),
+                   ln1=(1 + 0.2 * torch.randn(H, device=DEV, generator=g)).half(),
+                   ln2=(1 + 0.2 * torch.randn(H, device=DEV, generator=g)).half()) for _ in range(2)]
+    head, lnf = lin(H, V), (1 + 0.2 * torch.randn(H, device=DEV, generator=g)).half()
+    x0 = torch.randn(H, device=DEV, generator=g).half()
+
+    def buffers():
+        return dict(x=x0.clone(), qkv=torch.zeros(QKV, device=DEV).half(), u=torch.zeros(2 * I, device=DEV).half(),
+                    logits=torch.zeros(V, device=DEV).half())
+
+    def chain(emit, bf):
+        for b in blocks:
+            emit(bf["x"], *b["qkv"][:2], bf["qkv"], bias=b["qkv"][2], prologue=PRO_RMSNORM, norm_weight=b["ln1"], eps=1e-5)
+            emit(bf["qkv"], *b["o"][:2], bf["x"], resid=bf["x"])                # attention stand-in: q columns
+            emit(bf["x"], *b["w_in"][:2], bf["u"], prologue=PRO_RMSNORM, norm_weight=b["ln2"], eps=1e-5)
+            emit(bf["u"], *b["w_out"][:2], bf["x"], resid=bf["x"], prologue=PRO_SILU_GATE)
+        emit(bf["x"], *head[:2], bf["logits"], prologue=PRO_RMSNORM, norm_weight=lnf, eps=1e-5)
+
+    ref = buffers()
+    chain(lambda a, w, s, out, **kw: ops.gemv_fused_s4(a[:2 * w.shape[0] * (2 if kw.get("prologue") == PRO_SILU_GATE else 1)],
+                                                        w, s, out=out, **kw), ref)
+    torch.cuda.synchronize()
+    got = buffers()
+    prog = ops.DecodeProgram(torch.float16)
+    chain(lambda a, w, s, out, **kw: prog.add(a, w, s, out, **kw), got)
+    prog.build()
+    for rep in range(2):
+        got["x"].copy_(x0)
+        prog.run()
+        workers, failed = prog.status()
+        assert not failed and workers % 8 == 0 and workers >= 8
+        assert torch.isfinite(got["logits"].float()).all()
+        for k in ("x", "qkv", "u", "logits"):
+            assert torch.equal(got[k], ref[k]), f"run {rep}: {k} differs from the launch-per-linear chain"

@@ -7,6 +7,8 @@
 //   chainbench step   [ctx] [reps]          FUSED token step (cgq_decode_begin_w4, cgq_w4a16_gemv_fused,
 //                                           cgq_decode_attention): 142 launches, KV context ctx
 //   chainbench steptrace [ctx]              fused step once with the in-kernel timeline of the linears
+//   chainbench program [reps]               the `chain` linears as ONE persistent launch (cgq_program_*),
+//                                           checked bit for bit against the launch-per-linear chain
 //
 // Weights are random bytes (nibbles 1..15), scales ~ 1/(4.4*sqrt(K)) so the chain stays finite.
 // Every timing is CUDA events around `reps` replays of a CUDA graph of the launches.
@@ -298,8 +300,9 @@ int main(int argc, char** argv) {
   }
 
   // ---- chain
-  int M = argc > 2 ? atoi(argv[2]) : 1;
-  int reps = argc > 3 ? atoi(argv[3]) : 20;
+  const bool program_mode = !strcmp(mode, "program");
+  int M = (argc > 2 && !program_mode) ? atoi(argv[2]) : 1;
+  int reps = program_mode ? (argc > 2 ? atoi(argv[2]) : 20) : (argc > 3 ? atoi(argv[3]) : 20);
   std::vector<Lin> ls;
   size_t total = 0;
   for (int l = 0; l < LAYERS; ++l) {
@@ -319,6 +322,130 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&logits, (size_t)M * VOCAB * 2));
   fill_h<<<64, 256>>>(x, (size_t)M * H, 5, -1.f, 1.f);
   CK(cudaDeviceSynchronize());
+
+  if (program_mode) {
+    // the chain as (linear, input, output) steps; ping-pong hidden-state buffers so that no step overwrites
+    // its own input
+    struct Step { const Lin* l; const __half* in; __half* out; };
+    __half* xa;
+    CK(cudaMalloc(&xa, (size_t)H * 2));
+    std::vector<Step> steps;
+    const __half* in = x;
+    for (int l = 0; l < LAYERS; ++l) {
+      const Lin* p = &ls[4 * l];
+      __half* out = (l & 1) ? xa : b3;
+      steps.push_back({&p[0], in, b0});
+      steps.push_back({&p[1], b0, b1});
+      steps.push_back({&p[2], b1, b2});
+      steps.push_back({&p[3], b2, out});
+      in = out;
+    }
+    steps.push_back({&ls.back(), in, logits});
+    if (getenv("CGQ_DBG_OPS")) steps.resize(std::min<size_t>(steps.size(), atoi(getenv("CGQ_DBG_OPS"))));
+    const int n_out = steps.back().l->N;
+    // reference: one launch per linear
+    for (auto& sp : steps) run_lin(*sp.l, sp.in, sp.out, 1, sp.l->K, st);
+    CK(cudaStreamSynchronize(st));
+    std::vector<__half> want(n_out), got(n_out);
+    CK(cudaMemcpy(want.data(), steps.back().out, n_out * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemsetAsync(steps.back().out, 0, n_out * 2, st));   // (the stream is non-blocking: stay on it)
+    CK(cudaStreamSynchronize(st));
+    std::vector<cgq_linear_op> ops;
+    for (auto& sp : steps)
+      ops.push_back({sp.l->w, sp.l->s, sp.l->b, sp.in, sp.out, nullptr, nullptr, sp.l->N, sp.l->K, CGQ_PRO_NONE, 0.f});
+    uint64_t prog = 0;
+    CG(cgq_program_create(ops.data(), (int)ops.size(), CGQ_DTYPE_F16, &prog));
+    CG(cgq_program_run(prog, st));
+    CK(cudaStreamSynchronize(st));
+    int workers = 0, failed = 0;
+    CG(cgq_program_status(prog, &workers, &failed));
+    CK(cudaMemcpy(got.data(), steps.back().out, n_out * 2, cudaMemcpyDeviceToHost));
+    size_t diff = 0;
+    int first = -1;
+    for (int i = 0; i < n_out; ++i)
+      if (memcmp(&want[i], &got[i], 2) != 0) {
+        if (first < 0) first = i;
+        ++diff;
+      }
+    printf("program: %zu linears, %d workers, barrier failure flag %d, outputs differing from the launch-per-linear chain: %zu / %d",
+           ops.size(), workers, failed, diff, n_out);
+    if (first >= 0)
+      printf("  (first at %d: want %g got %g)", first, __half2float(want[first]), __half2float(got[first]));
+    printf("\n");
+    if (diff) {   // which 128-column tiles are wrong
+      printf("  wrong tiles:");
+      int run0 = -1, prev = -2;
+      for (int t = 0; t <= (n_out + 127) / 128; ++t) {
+        bool bad = false;
+        for (int i = t * 128; i < std::min(n_out, (t + 1) * 128); ++i) bad |= memcmp(&want[i], &got[i], 2) != 0;
+        if (bad && prev != t - 1) run0 = t;
+        if (!bad && prev == t - 1 && run0 >= 0) { printf(" %d-%d", run0, t - 1); run0 = -1; }
+        if (bad) prev = t;
+      }
+      printf("\n");
+    }
+    if (failed) return 2;
+    if (getenv("CGQ_PROGRAM_TRACE")) {   // timeline of ops 4..8 (second block) from a traced run
+      uint64_t* tr;
+      const size_t words = ops.size() * (size_t)workers * 4 + workers;
+      CK(cudaMalloc(&tr, words * 8));
+      CK(cudaMemsetAsync(tr, 0, words * 8, st));
+      cgq_debug_trace(tr);
+      CG(cgq_program_run(prog, st));
+      CK(cudaStreamSynchronize(st));
+      std::vector<uint64_t> h(words);
+      CK(cudaMemcpy(h.data(), tr, words * 8, cudaMemcpyDeviceToHost));
+      uint64_t t00 = ~0ull;
+      for (size_t i = 0; i < words; ++i)
+        if (h[i]) t00 = std::min(t00, h[i]);
+      {   // where did the scheduler put the workers?  workers per SM, and how many of the first 36 / 54 clusters
+        std::vector<int> per_sm(256, 0), a36(256, 0), a54(256, 0);
+        for (int c = 0; c < workers; ++c) {
+          const int sm = (int)h[ops.size() * (size_t)workers * 4 + c] - 1;
+          if (sm < 0 || sm >= 256) continue;
+          per_sm[sm]++;
+          if (c / 8 < 36) a36[sm]++;
+          if (c / 8 < 54) a54[sm]++;
+        }
+        int hist[3][9] = {{0}};
+        for (int sm = 0; sm < 256; ++sm)
+          if (per_sm[sm]) { hist[0][per_sm[sm]]++; hist[1][a36[sm]]++; hist[2][a54[sm]]++; }
+        const char* hn[3] = {"all workers", "clusters < 36 (qkv)", "clusters < 54 (w_in)"};
+        for (int k = 0; k < 3; ++k) {
+          printf("  SMs with n workers of %-22s:", hn[k]);
+          for (int n = 0; n <= 4; ++n) printf("  n=%d: %3d", n, hist[k][n]);
+          printf("\n");
+        }
+        t00 = ~0ull;
+        for (size_t i = 0; i < ops.size() * (size_t)workers * 4; ++i)
+          if (h[i]) t00 = std::min(t00, h[i]);
+      }
+      const char* nm[4] = {"barrier", "staged", "loopend", "stored"};
+      for (size_t op = 4; op < std::min<size_t>(ops.size(), 9); ++op) {
+        printf("op %zu (K=%d N=%d):\n", op, ops[op].K, ops[op].N);
+        for (int w = 0; w < 4; ++w) {
+          uint64_t mn = ~0ull, mx = 0; double sum = 0; int cnt = 0;
+          for (int c = 0; c < workers; ++c) {
+            uint64_t v = h[(op * workers + c) * 4 + w];
+            if (!v) continue;
+            mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)(v - t00); ++cnt;
+          }
+          if (cnt) printf("  %-8s n=%4d  min %8.2f  avg %8.2f  max %8.2f us\n", nm[w], cnt, (mn - t00) / 1e3, sum / cnt / 1e3, (mx - t00) / 1e3);
+        }
+      }
+    }
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    CG(cgq_program_run(prog, st));
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    float ms = time_graph(ge, st, reps);
+    CG(cgq_program_status(prog, &workers, &failed));
+    printf("program M=1: %.1f us/token  %.1f tok/s  %.1f GB/s algorithmic (%.3f GB)  1 launch, %zu linears  (failure flag %d)\n",
+           ms * 1e3, 1e3 / ms, total / (ms * 1e-3) / 1e9, total / 1e9, ops.size(), failed);
+    return diff != 0;
+  }
 
   uint64_t* trace = nullptr;
   const int kTraceWords = 8, kTraceCtas = 1024;
