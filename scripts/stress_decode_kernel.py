@@ -1,3 +1,5 @@
+"""Stress of the M = 8 decode kernel after an L2-warming launch (MODE=simple_each): how the ring-release race of
+DESIGN.md §3.1 was reproduced; tests/test_gpu_parity.py::test_decode_kernel_stress is the permanent check."""
 import os, sys, torch
 sys.path.insert(0, ".")
 from chatglm_q_b200 import ops

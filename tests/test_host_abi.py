@@ -142,3 +142,42 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libcgq.so")
     with pytest.raises(ImportError, match="no CPU / PyTorch fallback"):
         _lib.load()
+
+
+def test_fused_decode_wrapper_host_logic():
+    """FusedDecodeModel / accelerate() decide on the host which models the fused step can take (no GPU needed):
+    int4g32 buffers + fp16/bf16 + head size 64/128 -> fused; anything else -> TypeError / the graph wrapper."""
+    from types import SimpleNamespace as NS
+
+    import torch
+
+    from chatglm_q_b200.fused_decode import FusedDecodeModel, accelerate
+    from chatglm_q_b200.graph_decode import GraphDecodeModel
+
+    def lin(k, n, wdtype=torch.uint8, sdtype=torch.float16):
+        w = torch.zeros((k // 2, n), dtype=wdtype) if wdtype == torch.uint8 else torch.zeros((n, k), dtype=wdtype)
+        s = torch.zeros((k // 32, n), dtype=sdtype) if wdtype == torch.uint8 else torch.zeros(n, dtype=sdtype)
+        return NS(weight=w, weight_scale=s, bias=None)
+
+    def model(head=64, **kw):
+        cfg = NS(hidden_size=256, inner_hidden_size=384, head_hidden_size=head, num_multi_query_groups=2,
+                 num_attention_heads=256 // head, num_layers=1, vocab_size=256, max_sequence_length=64)
+        layer = NS(attn_ln=NS(weight=torch.ones(256), eps=1e-5), ffn_ln=NS(weight=torch.ones(256), eps=1e-5),
+                   attn=NS(qkv_proj=lin(256, 256 + 4 * head, **kw), o_proj=lin(256, 256, **kw)),
+                   ffn=NS(w_in=lin(256, 768, **kw), w_out=lin(384, 256, **kw)))
+        return NS(config=cfg, layers=[layer], final_ln=NS(weight=torch.ones(256), eps=1e-5), lm_head=lin(256, 256, **kw),
+                  word_embedding=NS(weight=torch.zeros((128, 256), dtype=torch.uint8),
+                                    weight_scale=torch.zeros((8, 256), dtype=torch.float16)),
+                  freqs_cis_cache=torch.zeros((64, head), dtype=torch.float16))
+
+    fused = FusedDecodeModel(model(), max_len=1000)
+    assert fused.max_len == 63 and fused.launches_per_step() == 7          # window clipped to the rotary table
+    assert isinstance(accelerate(model()), FusedDecodeModel)
+    for bad in (model(wdtype=torch.int8), model(sdtype=torch.float32), model(head=32)):
+        try:
+            FusedDecodeModel(bad)
+        except TypeError:
+            pass
+        else:
+            raise AssertionError("FusedDecodeModel accepted a model the fused step cannot take")
+        assert isinstance(accelerate(bad), GraphDecodeModel)
