@@ -137,14 +137,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- synthetic weights
-def make_w4(torch, k: int, n: int, bias: bool, device, gen):
+def make_w4(torch, k: int, n: int, bias: bool, device, gen, k_full: int = None):
     """Random packed nibbles in 1..15 (what quantize_int4 emits: zero-mean q-8 in -7..7, so a chain
-    of linears neither drifts nor overflows) + group scales sized for unit gain."""
+    of linears neither drifts nor overflows) + group scales sized for unit gain.  A row-parallel shard
+    (k rows of a k_full-row weight) keeps the full linear's scale, so that the all-reduced sum has unit gain."""
     lo = torch.randint(1, 16, (k // 2, n), dtype=torch.uint8, device=device, generator=gen)
     hi = torch.randint(1, 16, (k // 2, n), dtype=torch.uint8, device=device, generator=gen)
     w = lo | (hi << 4)
     del lo, hi
-    s = (torch.rand((k // 32, n), device=device, generator=gen) * 0.5 + 0.75) * (1.0 / (4.4 * k ** 0.5))
+    s = (torch.rand((k // 32, n), device=device, generator=gen) * 0.5 + 0.75) * (1.0 / (4.4 * (k_full or k) ** 0.5))
     b = (torch.randn(n, device=device, generator=gen) * 0.02).half() if bias else None
     return w, s.half(), b
 
@@ -159,10 +160,12 @@ class TokenStep:
         self.hints = int(os.environ.get("CGQ_PF_MB", "0") or 0) > 0    # experimental L2 prefetch hints: off
         self.plan, block, head = token_linears(world, rank)
         gen = torch.Generator(device=device).manual_seed(1234 + rank)
-        self.layers = [[(name, *make_w4(torch, k, n, bias, device, gen)) for name, k, n, bias in block]
+        k_full = {"o_proj": H, "w_out": INNER}          # row-parallel linears: the shard keeps the full-K scale
+        self.layers = [[(name, *make_w4(torch, k, n, bias, device, gen, k_full.get(name))) for name, k, n, bias in block]
                        for _ in range(LAYERS)]
         self.head = make_w4(torch, head[1], head[2], False, device, gen)
-        self.x = torch.randn((m, H), device=device, generator=gen).half()
+        # the hidden state is replicated: the same on every rank
+        self.x = torch.randn((m, H), device=device, generator=torch.Generator(device=device).manual_seed(99)).half()
         self.bytes = LAYERS * sum(w4_bytes(m, k, n, b) for _, k, n, b in block) + w4_bytes(m, head[1], head[2], False)
         self.launches = LAYERS * 4 + 1
         self.kq = block[1][1]      # o_proj K on this rank
@@ -472,6 +475,11 @@ def run_reference_arm(args):
 def run_own_arm(args):
     import torch
 
+    if os.environ.get("CGQ_BENCH_DEBUG"):       # where is every rank after N seconds? (hang triage)
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["CGQ_BENCH_DEBUG"]), exit=True)
+
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -575,14 +583,33 @@ def run_own_arm(args):
                                     "sample": f"{len(ts)} x (1 of 28 blocks + lm_head) at M=1 fp16 through the reference "
                                               f"CPU path, token time = 28 x block + lm_head; {wall:.1f} s of CPU work"}
     else:
-        # e2e at N>1: the same TP step fed from pinned host memory and read back every step
+        # e2e at N>1: the same TP step fed from pinned host memory and read back every step.  A watchdog makes
+        # sure a stuck collective can never hang the bench: the line is then printed without the e2e number.
+        def bail():
+            if rank == 0:
+                line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": H * 2, "d2h_bytes_per_step": 8,
+                               "note": "TP e2e leg did not finish within 120 s and was abandoned"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(120.0, bail)
+        dog.daemon = True
+        dog.start()
         line_e2e = tp_e2e(torch, device, world, rank, args)
+        dog.cancel()
         if rank == 0:
             line["e2e"] = line_e2e
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # NCCL's communicator teardown can block forever after CUDA graphs that captured collectives
+        # (seen on 2 x B200: both ranks stuck in destroy_process_group after the line was printed): leave
+        # through a barrier and a hard exit instead -- the result is already out.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def tp_e2e(torch, device, world, rank, args):
@@ -591,8 +618,9 @@ def tp_e2e(torch, device, world, rank, args):
     import torch.distributed as dist
 
     step = TokenStep(torch, device, world, rank)
-    host_x = torch.randn(1, H).half().pin_memory()
-    with torch.no_grad():
+    host_x = torch.randn(1, H, generator=torch.Generator().manual_seed(7)).half().pin_memory()
+    stream = torch.cuda.Stream(device=device)      # (same kind of stream as the timed region, not the legacy one)
+    with torch.cuda.stream(stream), torch.no_grad():
         for _ in range(3):
             step.x.copy_(host_x, non_blocking=True)
             int(step.run().argmax().item())
