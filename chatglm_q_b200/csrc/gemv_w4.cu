@@ -15,8 +15,11 @@
 //     dependent launch the next kernel's producers fill their rings with weights (which do not
 //     depend on the previous kernel) while this kernel is still computing;
 //   * one producer lane per CTA feeds an S-deep shared-memory ring with TMA: a [64 x 128] byte
-//     tile of packed weights (128-byte swizzle), the [4 x 128] scale tile, and the matching
-//     128-k slice of each activation row (cp.async.bulk), all landing on one mbarrier;
+//     tile of packed weights (128-byte swizzle) and the [4 x 128] scale tile on one mbarrier.  The ring
+//     carries weights only.  Activations: M == 1 -- the consumers stage the CTA's k-band of the row ONCE
+//     with plain L2 loads right after the dependency wait, through an optional fused prologue (RMSNorm
+//     of the whole row, SiLU*gate), and the residual is added in the epilogue (cgq_w4a16_gemv_fused);
+//     M > 1 -- every lane reads its own B-fragment words from L2 one stage ahead of use;
 //   * 4 consumer warps each own one 32-k quantisation group of the stage.  A lane reads two
 //     16-byte runs (16 columns, packed rows 2t and 2t+1), and one PRMT per column makes the
 //     32-bit word [byte(r), -, byte(r+1), -], whose masked halves are exactly the (k, k') pairs
@@ -24,10 +27,14 @@
 //     B fragment (<= 8 tokens), accumulation is fp32 in the tensor core;
 //   * the group scale is applied to the group's fp32 partial sum:  out = Σ_g s_g · Σ_{k∈g} a_k (q_k-8)
 //     (more accurate than the reference's per-element fp16 rounding; within the 1e-2 parity bar);
-//   * fp16 fast variant ("trick"): the masked nibble IS an fp16 subnormal q·2^-24 (q·2^-20 for
-//     the high nibble, compensated by scaling the odd-k activations by 2^-4), so no int->fp
-//     conversion is executed at all; the -8 offset becomes -8·Σ_{k∈g} a_k, obtained from one
-//     extra MMA against a constant fragment.
+//   * M == 1, fp16 ("trick"): the masked nibble IS an fp16 subnormal q·2^-24 (q·2^-20 for the high
+//     nibble, compensated by scaling the odd-k activations by 2^-4), so no int->fp conversion is
+//     executed at all; the -8 offset becomes -8·Σ_{k∈g} a_k, obtained from one extra MMA against a
+//     constant fragment.  bf16 and every M > 1 convert exactly ((1024+q) - 1032);
+//   * a ring slot is released with ptx::mbar_arrive_after_loads: the mbarrier address depends on the
+//     registers loaded from the slot, so the arrive cannot overtake an ld.shared that is still queued
+//     (the producer answers a release with a TMA write into the same slot; a refill that hit L2 used to
+//     land before the stage's scale loads in ~10 % of the M = 8 launches).
 #include <stdlib.h>
 
 #include <type_traits>

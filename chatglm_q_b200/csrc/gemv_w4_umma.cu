@@ -335,7 +335,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       uint4 sc = make_uint4(0, 0, 0, 0);
       if (lane < 16) sc = ptx::lds128(Wsm + s * STAGE_BYTES + W_BYTES + q * (BN * 2) + lane * 16);
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&empty_tma[s]);   // packed bytes and scales are in registers
+      // release only once the loads from the slot have returned (ptx::mbar_arrive_after_loads)
+      if (lane == 0)
+        ptx::mbar_arrive_after_loads(&empty_tma[s], r[0][0] | r[GPS - 1][3] | sc.x, static_cast<uint32_t>(p.K) >> 31);
       ptx::mbar_wait(&d_empty[ss], sph ^ 1);             // previous user of the slot has been multiplied and read
       ptx::tc_fence_after();
       if (lane < 16) ptx::sts128(Ssl + ss * SC_STAGE + q * (BN * 2) + lane * 16, sc);

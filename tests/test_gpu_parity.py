@@ -423,3 +423,28 @@ def test_decode_kernel_stress(n):
                 assert_parity(from_torch(y), from_torch(ref), f"stress M={m} N={n}")
             else:
                 assert torch.equal(y, first), f"M={m} N={n}: launch {rep} differs from launch 0"
+
+
+# ------------------------------------------------------------------ tensor-parallel shard shapes
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tp_shard_shapes_on_the_decode_kernel(world):
+    """Every per-rank linear of the TP plan (column slices of qkv / w_in / lm_head, k-row slices of o_proj / w_out:
+    K = 512 .. 6848, 54/53-group splits at T=8) through the decode kernel at M=1 against the CUDA-core kernel."""
+    from chatglm_q_b200 import tp
+
+    g = torch.Generator(device=DEV).manual_seed(world)
+    seen = set()
+    for rank in {0, world - 1}:
+        plan = tp.plan_block(world, rank)
+        shapes = [(4096, plan.qkv.n_out(4608)), (plan.o.k_in(4096), 4096), (4096, plan.w_in.n_out(27392)),
+                  (plan.w_out.k_in(13696), 4096), (4096, plan.lm_head.n_out(65024))]
+        for k, n in shapes:
+            if (k, n) in seen:
+                continue
+            seen.add((k, n))
+            bq = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV, generator=g)
+            s = ((torch.rand((k // 32, n), device=DEV, generator=g) * 0.5 + 0.75) / (4.4 * k ** 0.5)).half()
+            a = torch.randn((1, k), device=DEV, generator=g).half()
+            y = ops.dynamic_quant_matmul_s4(a, bq, s)
+            assert_parity(from_torch(y), from_torch(ops.dynamic_quant_matmul_s4(a, bq, s, impl=ops.IMPL_SIMPLE)),
+                          f"T={world} rank {rank} K={k} N={n}")
