@@ -283,7 +283,87 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     for (int i = 0; i < NT; ++i) tot[j][i] = 0.f;
 
   int slot = 0, phase = 0;
-  {
+  constexpr bool kLdsm = kM1 && kTrick;   // fp16, one token: unpack through ldmatrix, see below
+  if constexpr (kLdsm) {
+    // The integer-ALU pipe (16 lanes per sub-partition) is this kernel's scarcest resource, so
+    // the byte transposition is left to the load unit: ldmatrix.trans on 8x8 tiles of 16-bit elements gives
+    // lane (g, tig) the word [B(2t,2g), B(2t,2g+1), B(2t+1,2g), B(2t+1,2g+1)] (B = packed byte, rows 2t, 2t+1
+    // of the tile, columns 2g, 2g+1 of a 16-column block).  With z = word >> 8 the four A-fragment registers
+    // of an m16n8k16 are word & 0x000F000F, z & 0x000F000F (low nibbles of the two columns, q * 2^-24 as fp16
+    // subnormals) and word & 0x00F000F0, z & 0x00F000F0 (high nibbles, q * 2^-20, the odd-k activations carry
+    // the 2^-4): one shift and four masks per 8 nibbles where the PRMT path needs two permutes and four masks.
+    // (A nibble may not sit above bit 7 of its 16-bit lane: the bit pattern n is only the number n * 2^-24
+    // while n < 2^11.)  MMA row g <-> column 16 j + 2 g, row g + 8 <-> column 16 j + 2 g + 1.
+    const bool has_tok = g == 0;
+    const int li = lane & 7, lm = lane >> 3;           // ldmatrix: this lane addresses row li of matrix lm
+    // matrices of one ldmatrix.x4: (row tile lm & 1, 16-byte column chunk c0 + (lm >> 1))
+    uint32_t ld_off[4];   // loop-invariant: row address + swizzled 16-byte chunk of this lane's four loads
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      ld_off[c] = static_cast<uint32_t>((16 * warp + 8 * (lm & 1) + li) * BN + (((2 * c + (lm >> 1)) ^ li) << 4));
+    for (int it = 0; it < n_units; ++it) {
+      ptx::mbar_wait(&full[slot], phase);
+      if (it == 0 && threadIdx.x == 0) stamp(p, 3);
+      const uint32_t wrow = Wsm + slot * W_BYTES;
+      const uint32_t srow = Ssm + slot * S_BYTES + warp * (BN * 2) + g * 4;
+      uint32_t w[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t addr = wrow + ld_off[c];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(w[c][0]), "=r"(w[c][1]), "=r"(w[c][2]), "=r"(w[c][3])
+                     : "r"(addr));
+      }
+      uint32_t sw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sw[j] = ptx::lds32(srow + j * 32);   // scales of columns 16 j + 2 g, + 1
+      float grp[8][4];
+      float ag[4];
+      const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        uint2 av = make_uint2(0u, 0u);
+        if (has_tok) av = ptx::lds64(Aband + (it * KSTAGE + 32 * warp + 4 * tig) * 2 + 32 * b);
+        const uint32_t b0 = __byte_perm(av.x, av.y, 0x5410);   // (a[+0], a[+2]) <-> low nibbles of rows 2t, 2t+1
+        const uint32_t b1 = h2_mul(__byte_perm(av.x, av.y, 0x7632), 0x2C002C00u);   // (a[+1], a[+3]) * 2^-4 <-> high nibbles
+        const uint32_t ones[4] = {0x3C003C00u, 0x3C003C00u, 0x4C004C00u, 0x4C004C00u};  // 1,1 | 16,16
+        if (b == 0)
+          ptx::mma_16816(ag, ones, b0, b1, zero4, T());
+        else
+          ptx::mma_16816(ag, ones, b0, b1, ag, T());
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t x = w[j >> 1][(j & 1) * 2 + b];
+          const uint32_t z = x >> 8;
+          const uint32_t a[4] = {x & 0x000F000Fu, z & 0x000F000Fu, x & 0x00F000F0u, z & 0x00F000F0u};
+          if (b == 0)
+            ptx::mma_16816(grp[j], a, b0, b1, zero4, T());
+          else
+            ptx::mma_16816(grp[j], a, b0, b1, grp[j], T());
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        ptx::mbar_arrive_after_loads(&empty[slot], w[0][0] | w[1][0] | w[2][0] | w[3][0] | sw[7], rt_zero);
+      const float c0 = -8.f * ag[0];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        union {
+          uint32_t u;
+          T h[2];
+        } cv;
+        cv.u = sw[j];
+        const float t0 = fmaf(grp[j][0], 16777216.f, c0);   // column 16 j + 2 g
+        const float t2 = fmaf(grp[j][2], 16777216.f, c0);   // column 16 j + 2 g + 1
+        tot[j][0] = fmaf(DT<T>::to_f(cv.h[0]), t0, tot[j][0]);
+        tot[j][1] = fmaf(DT<T>::to_f(cv.h[1]), t2, tot[j][1]);
+      }
+      if (++slot == S) {
+        slot = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
   // B fragment: lane (g, tig) supplies token g's activations a[k0+4t .. k0+4t+3] of both halves of the
   // warp's 32-k group, read from L2 one stage ahead of use (zeros for g >= M and for k >= K)
   const bool has_tok = kM1 ? (g == 0) : (g < p.M);
@@ -416,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int tok = kM1 ? 0 : 2 * tig + (i & 1);
-      const int col = 16 * g + 2 * j + (kM1 ? i : (i >> 1));
+      const int col = kLdsm ? 16 * j + 2 * g + i : 16 * g + 2 * j + (kM1 ? i : (i >> 1));
       const bool ok = kM1 ? (tig == 0) : (tok < p.M);
       if (ok) red[(warp * MR + tok) * BN + col] = tot[j][i];
     }
