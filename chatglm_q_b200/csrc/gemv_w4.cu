@@ -314,9 +314,6 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
                      : "=r"(w[c][0]), "=r"(w[c][1]), "=r"(w[c][2]), "=r"(w[c][3])
                      : "r"(addr));
       }
-      uint32_t sw[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sw[j] = ptx::lds32(srow + j * 32);   // scales of columns 16 j + 2 g, + 1
       float grp[8][4];
       float ag[4];
       const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -342,6 +339,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
             ptx::mma_16816(grp[j], a, b0, b1, grp[j], T());
         }
       }
+      uint32_t sw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sw[j] = ptx::lds32(srow + j * 32);   // scales of columns 16 j + 2 g, + 1
       __syncwarp();
       if (lane == 0)
         ptx::mbar_arrive_after_loads(&empty[slot], w[0][0] | w[1][0] | w[2][0] | w[3][0] | sw[7], rt_zero);
