@@ -358,7 +358,16 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     graphed, graphed_prefill, _ = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
                                                      tok, device=device, time_log=False))
     fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32)
-    fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+    fused_ref_sampler, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+    # the sampler is a module global of the reference too (decoder.py:12, resolved at :85): rebind it to the
+    # one-launch cgq_top_p_sample (same signature, same token for the same seed) -- the headline configuration
+    install("chatglm_q", sampler=True)
+    try:
+        fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+    finally:
+        from chatglm_q_b200.install import uninstall
+        uninstall("chatglm_q")
+        install("chatglm_q")
     # device time of the fused step alone (graph replays between CUDA events; the KV window is rewound so
     # every replay attends over the same context length as the middle of the generation)
     dev_us = None
@@ -383,8 +392,12 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
                    f"the unmodified int4g32 ChatGLM2Model (its module buffers in place): one CUDA-graph replay of {launches} "
                    f"C-ABI launches per token (fused RMSNorm/SiLU-gate/residual dequant-matmuls + RoPE/KV/attention kernel, "
                    f"PDL-chained); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after the first / "
-                   f"their summed wall time (each step: H2D token id, graph replay, reference top-p sampling, .item() D2H)",
+                   f"their summed wall time (each step: H2D token id, graph replay, top-p sampling by cgq_top_p_sample "
+                   f"bound to the decoder's top_p_sampling global -- 2 launches instead of the reference's ~15 torch kernels "
+                   f"and multinomial's host sync --, .item() D2H)",
             "prefill_s": prefill_s, "tokens": n_tok,
+            "fused_step_reference_sampler": {"value": fused_ref_sampler,
+                                             "how": "same fused step, the reference's own torch top_p_sampling"},
             "fused_step_device_us": dev_us, "fused_step_launches": launches,
             "graphed_reference_forward": {"value": graphed, "prefill_s": graphed_prefill,
                                           "how": "same decoder, unmodified model forward captured in one CUDA graph "

@@ -33,6 +33,8 @@ SYMBOLS = {
                                     c_int, c_void_p, c_void_p]),
     "cgq_decode_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p]),
+    "cgq_top_p_sample": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "cgq_w4_unpack_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "cgq_w4_dequant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cgq_w4_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -179,7 +179,7 @@ static int check_workspace(const char* fn, void* ws, size_t bytes) {
 
 using namespace cgq;
 
-extern "C" int cgq_version(void) { return (0 << 16) | 1; }
+extern "C" int cgq_version(void) { return (0 << 16) | 2; }
 extern "C" const char* cgq_last_error(void) { return g_err; }
 extern "C" size_t cgq_workspace_bytes(void) { return kWorkspaceBytes; }
 extern "C" void cgq_debug_trace(void* device_buffer) { g_trace = device_buffer; }

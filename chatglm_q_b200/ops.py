@@ -253,6 +253,59 @@ def decode_attention(qkv: Tensor, freqs: Tensor, k_cache: Tensor, v_cache: Tenso
     return out
 
 
+# ---------------------------------------------------------------------- sampling
+def _sample_rows(logits: Tensor, top_k: int, top_p: float, temperature: float, want_token: bool,
+                 q: Tensor = None):
+    assert logits.get_device() >= 0, "top_p_sampling: CUDA logits only (no CPU fallback on this path)"
+    assert logits.dim() >= 1 and logits.shape[-1] >= 1
+    assert temperature > 0 and top_p >= 0 and top_k >= 1
+    code = _dtype_code(logits)
+    V = logits.shape[-1]
+    k = min(int(top_k), V)
+    rows = logits.reshape(-1, V)
+    if rows.stride(1) != 1:
+        rows = rows.contiguous()
+    n = rows.shape[0]
+    lib = _lib.load()
+    with torch.cuda.device(logits.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if want_token:
+            # the variates torch.multinomial(probs, 1) draws for itself: empty_like(probs).exponential_(1)
+            if q is None:
+                q = torch.empty((n, k), dtype=torch.float32, device=logits.device).exponential_(1)
+            else:
+                assert q.dtype == torch.float32 and q.numel() == n * k and q.device == logits.device
+                q = q.reshape(n, k).contiguous()
+            token = torch.empty(n, dtype=torch.int64, device=logits.device)
+            for r in range(n):
+                _lib.check(lib.cgq_top_p_sample(
+                    rows[r].data_ptr(), V, code, int(top_k), float(top_p), float(temperature),
+                    q[r].data_ptr(), token[r].data_ptr(), None, None, stream))
+            return token.reshape(logits.shape[:-1])
+        probs = torch.empty((n, k), dtype=torch.float32, device=logits.device)
+        indices = torch.empty((n, k), dtype=torch.int64, device=logits.device)
+        for r in range(n):
+            _lib.check(lib.cgq_top_p_sample(
+                rows[r].data_ptr(), V, code, int(top_k), float(top_p), float(temperature),
+                None, None, probs[r].data_ptr(), indices[r].data_ptr(), stream))
+        return probs.reshape(*logits.shape[:-1], k), indices.reshape(*logits.shape[:-1], k)
+
+
+def top_p_sampling(logits: Tensor, top_k=100, top_p=0.8, temperature=1.0, *, q: Tensor = None) -> Tensor:
+    """Drop-in for chatglm_q.decoder.top_p_sampling (chatglm_q/decoder.py:12-27): logits (..., V) fp16 / bf16 on
+    the GPU -> sampled token ids (...) int64.  Two launches per call (the Exp(1) draw torch.multinomial would make,
+    then cgq_top_p_sample per row) instead of ~15 and a host synchronisation; with the same torch seed it
+    returns the token the reference returns.  `q` (keyword-only, not in the reference): the Exp(1) variates
+    (..., min(top_k, V)) fp32 to use instead of drawing them -- reproducible sampling for tests."""
+    return _sample_rows(logits, top_k, top_p, temperature, True, q)
+
+
+def top_p_distribution(logits: Tensor, top_k=100, top_p=0.8, temperature=1.0) -> tuple[Tensor, Tensor]:
+    """The (probs, indices) pair chatglm_q/decoder.py:14-22 hands to torch.multinomial / torch.gather:
+    top_k probabilities, descending, masked by top_p and renormalised (fp32), and their vocabulary ids."""
+    return _sample_rows(logits, top_k, top_p, temperature, False)
+
+
 def prefetch_next_s4(b: Tensor, b_scale: Tensor) -> None:
     """One-shot hint (cgq_prefetch_next_w4): the NEXT int4 decode launch of this thread also streams the
     leading part of THIS weight — the one the launch after it will read — from HBM into L2."""

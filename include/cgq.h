@@ -217,6 +217,26 @@ int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void*
                          int dtype, void* stream);
 
 /*
+ * ---- Token sampling ---------------------------------------------------
+ * chatglm_q.decoder.top_p_sampling (chatglm_q/decoder.py:12-27) for ONE logits row, in one launch:
+ *   probs = softmax(float(logits) / temperature) over the whole vocabulary        (:14)
+ *   the top_k largest, descending (ties: lower vocabulary index first)            (:15-17)
+ *   probs[(cumsum(probs) - probs) > top_p] = 0;  probs /= sum(probs)              (:20-22)
+ *   token = indices[argmax(probs / q)]   -- what torch.multinomial(probs, 1) computes from its
+ *           Exp(1) variates q (:25-26); the caller draws q ([min(top_k, V)] fp32, e.g.
+ *           torch.empty(k).exponential_(1): the same generator call multinomial makes, so the same
+ *           seed gives the reference's token).
+ *   logits  [V] dtype (fp16 / bf16: the exact radix select runs on 16-bit keys), 2-byte aligned
+ *   q       [k] fp32 or NULL (NULL: only the distribution is produced; `token` must be NULL)
+ *   token   [1] int64 or NULL;  probs [k] fp32 or NULL;  indices [k] int64 or NULL,  k = min(top_k, V)
+ * Limits: top_k <= 1024; the row must fit in shared memory (V <= ~90 000); temperature > 0, top_p >= 0.
+ * Deviation from the reference: the order is taken on the LOGITS, the reference sorts the fp32
+ * probabilities -- identical unless two different logits round to the same probability.
+ */
+int cgq_top_p_sample(const void* logits, int V, int dtype, int top_k, float top_p, float temperature,
+                     const float* q, int64_t* token, float* probs, int64_t* indices, void* stream);
+
+/*
  * Profiling aid (no reference counterpart): the NEXT decode-kernel launch issued by the calling
  * thread writes a per-CTA timeline (8 x uint64 %globaltimer stamps per CTA, first 1024 CTAs:
  * entry, producer start, consumer dependency wait passed, first data, loop end, exit,

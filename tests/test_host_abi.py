@@ -48,6 +48,14 @@ def test_abi_argument_errors_without_gpu():
     assert rc == -1
     with pytest.raises(_lib.CgqError):
         _lib.check(rc)
+    # sampler: top_k < 1, temperature <= 0, dtype code, top_k > 1024, row too large, token without variates
+    assert lib.cgq_top_p_sample(P, 1000, 0, 0, 0.8, 1.0, None, None, P, P, None) == -1
+    assert lib.cgq_top_p_sample(P, 1000, 0, 10, 0.8, 0.0, None, None, P, P, None) == -1
+    assert lib.cgq_top_p_sample(P, 1000, 7, 10, 0.8, 1.0, None, None, P, P, None) == -2
+    assert lib.cgq_top_p_sample(P, 5000, 0, 2000, 0.8, 1.0, None, None, P, P, None) == -1
+    assert lib.cgq_top_p_sample(P, 200000, 0, 10, 0.8, 1.0, None, None, P, P, None) == -1
+    assert lib.cgq_top_p_sample(P, 1000, 0, 10, 0.8, 1.0, None, P, None, None, None) == -1
+    assert b"variates" in lib.cgq_last_error()
 
 
 def test_product_never_imports_oracle():
@@ -55,6 +63,21 @@ def test_product_never_imports_oracle():
     for f in (ROOT / "chatglm_q_b200").rglob("*"):
         if f.suffix in {".py", ".cu", ".cuh", ".h"}:
             assert not pat.search(f.read_text()), f"{f} references the oracle"
+
+
+def test_sampler_host_checks():
+    """ops.top_p_sampling keeps the reference signature (decoder.py:12) and refuses what the kernel cannot take."""
+    import inspect
+
+    import torch
+
+    from chatglm_q_b200 import ops
+
+    sig = inspect.signature(ops.top_p_sampling)
+    assert [(n, p.default) for n, p in sig.parameters.items() if p.kind is p.POSITIONAL_OR_KEYWORD] == [
+        ("logits", inspect.Parameter.empty), ("top_k", 100), ("top_p", 0.8), ("temperature", 1.0)]
+    with pytest.raises(AssertionError):
+        ops.top_p_sampling(torch.zeros(100, dtype=torch.float16))          # CPU tensor: no fallback
 
 
 def test_host_checks_mirror_reference_asserts():
@@ -130,6 +153,16 @@ def test_install_rebinds_reference_globals():
         install.uninstall(pkg)
         assert mods[f"{pkg}.int4.qlinear"]._dynamic_quant_matmul_impl is sentinel
         assert mods[f"{pkg}.int8.qlinear"].KERNEL_IMPL == "none"
+        # decoder.top_p_sampling is a module global too (decoder.py:12, resolved at :85): opt-in rebind
+        dec = types.ModuleType(f"{pkg}.decoder")
+        dec.top_p_sampling = sentinel
+        sys.modules[dec.__name__] = mods[dec.__name__] = dec
+        install.install(pkg)
+        assert dec.top_p_sampling is sentinel
+        install.install(pkg, sampler=True)
+        assert dec.top_p_sampling is ops.top_p_sampling
+        install.uninstall(pkg)
+        assert dec.top_p_sampling is sentinel
     finally:
         for name in mods:
             sys.modules.pop(name, None)

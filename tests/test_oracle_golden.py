@@ -154,3 +154,39 @@ def test_decode_step_oracle_matches_reference_model():
     for i in range(cfg["n_layers"]):
         assert_parity(kv[i][0], fx[f"final_k{i}"].astype(np.float32), f"k cache layer {i}", rtol=2e-2)
         assert_parity(kv[i][1], fx[f"final_v{i}"].astype(np.float32), f"v cache layer {i}", rtol=2e-2)
+
+
+# ---------------------------------------------------------------------- sampler
+def _sampling_cases():
+    fx = dict(np.load(Path(__file__).resolve().parent / "golden" / "sampling.npz"))
+    for entry in fx["cases"]:
+        name, dtype = str(entry).split(":")
+        bits = fx[f"{name}_logits_bits"]
+        logits = orc.bf16_from_bits(bits) if dtype == "bfloat16" else bits.view(np.float16).astype(np.float32)
+        top_k, top_p, temp = fx[f"{name}_params"]
+        yield name, dtype, logits, int(top_k), float(top_p), float(temp), fx
+
+
+def test_sampling_oracle_matches_reference_distribution_and_token():
+    """oracle/sampling_oracle.py against what the unmodified chatglm_q.decoder.top_p_sampling handed to
+    torch.multinomial / torch.gather (tests/golden/make_golden_sampling.py), and against the token it returned."""
+    from oracle import sampling_oracle as so
+
+    n = 0
+    for name, _, logits, top_k, top_p, temp, fx in _sampling_cases():
+        p, idx = so.top_p_distribution(logits, top_k, top_p, temp)
+        ref_p, ref_idx = fx[f"{name}_probs"], fx[f"{name}_indices"]
+        assert p.shape == ref_p.shape, name
+        np.testing.assert_allclose(p, ref_p, rtol=2e-6, atol=1e-9, err_msg=name)
+        # the same probabilities at every rank; the same ids wherever the probability is not tied
+        assert np.array_equal(logits[idx], logits[ref_idx]), name
+        untied = np.ones(len(idx), bool)
+        lv = logits[ref_idx]
+        untied[1:] &= lv[1:] != lv[:-1]
+        untied[:-1] &= lv[:-1] != lv[1:]
+        edge = logits[ref_idx[-1]]
+        untied &= lv != edge                      # the boundary value may have more holders than slots
+        assert np.array_equal(idx[untied], ref_idx[untied]), name
+        assert so.sample_with(ref_p, ref_idx, fx[f"{name}_q"]) == int(fx[f"{name}_token"]), name
+        n += 1
+    assert n >= 7
