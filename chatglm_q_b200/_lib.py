@@ -24,6 +24,8 @@ SYMBOLS = {
     "cgq_debug_trace": (None, [c_void_p]),
     "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "cgq_handover_next": (c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
+    "cgq_w4_gemv_tiles": (c_int, [c_int]),
     "cgq_program_create": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "cgq_program_run": (c_int, [ctypes.c_uint64, c_void_p]),
     "cgq_program_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p]),

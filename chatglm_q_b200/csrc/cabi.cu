@@ -268,6 +268,17 @@ extern "C" int cgq_prefetch_next_w4(const uint8_t* Wq, const void* scale, int N,
   return CGQ_OK;
 }
 
+extern "C" int cgq_handover_next(const uint32_t* wait_ctr, uint32_t wait_count, uint32_t* signal_ctr) {
+  if (((reinterpret_cast<uintptr_t>(wait_ctr) | reinterpret_cast<uintptr_t>(signal_ctr)) & 3) ||
+      (wait_ctr != nullptr && wait_count == 0)) {
+    set_error("cgq_handover_next: counters must be 4-byte aligned and wait_count > 0 with a wait counter");
+    return CGQ_ERR_MISALIGNED;
+  }
+  set_w4_handover(wait_ctr, wait_count, signal_ctr);
+  return CGQ_OK;
+}
+extern "C" int cgq_w4_gemv_tiles(int N) { return N > 0 ? w4_gemv_tiles(N) : 0; }
+
 extern "C" int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void* scale,
                                     const void* bias, const void* resid, void* C, int N, int K,
                                     int group, int dtype, int prologue, const void* norm_w,

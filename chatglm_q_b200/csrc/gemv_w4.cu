@@ -83,6 +83,11 @@ struct Params {
   const uint8_t* pf_w;
   const uint8_t* pf_s;   // scales, 2 bytes per element
   int pf_N, pf_rows, pf_groups, pf_SPT, pf_Z, pf_depth, pf_ppc_w, pf_ppc, pf_pieces;
+  // tile-granular hand-over (cgq_handover_next, kHand kernels only): the consumers acquire-poll `wait_ctr` until it
+  // reaches `wait_count` INSTEAD of griddepcontrol.wait; every stored output tile release-increments `signal_ctr`
+  const unsigned* wait_ctr;
+  unsigned wait_count;
+  unsigned* signal_ctr;
 };
 constexpr int kPfPiece = 16384;
 
@@ -120,7 +125,44 @@ __device__ __forceinline__ void stamp(const Params& p, int slot) {
   }
 }
 
-template <typename T, bool kTrick, bool kM1, int kPro>
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Activations of this launch are complete.  Default: the whole previous grid has drained and flushed
+// (griddepcontrol.wait).  Hand-over variant: every output tile of the producing launch has been stored and
+// announced -- no wait for the grid to drain (the ~1.2 us between its last CTA's exit and the wait returning).
+// One lane per warp polls; the spin is bounded (a lost producer gives wrong numbers, never a hung device).
+template <bool kHand>
+__device__ __forceinline__ void wait_inputs(const Params& p) {
+  if constexpr (kHand) {
+    if (p.wait_ctr != nullptr) {
+      if ((threadIdx.x & 31) == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_gpu(p.wait_ctr) < p.wait_count && ++spins < (1u << 15)) __nanosleep(20);   // <= ~25 ms
+      }
+      __syncwarp();
+      return;
+    }
+  }
+  ptx::pdl_wait_prior_grid();
+}
+// the calling (consumer) threads have stored one output tile: announce it
+template <bool kHand>
+__device__ __forceinline__ void signal_tile(const Params& p) {
+  if constexpr (kHand) {
+    if (p.signal_ctr != nullptr) {
+      ptx::named_bar_sync(1, CW * 32);
+      if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.signal_ctr), "r"(1u) : "memory");
+      }
+    }
+  }
+}
+
+template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
 __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     w4_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmS,
                    const Params p) {
@@ -224,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         const int c = tid + CW * 32 * i;
         wr[i] = (single && c >= c_lo && c < c_hi && c < nchunk) ? ldnc128(nw + c * 8) : zero;
       }
-      ptx::pdl_wait_prior_grid();
+      wait_inputs<kHand>(p);
       if (threadIdx.x == 0) stamp(p, 2);
       float ss = 0.f;
       for (int cb = 0; cb < nchunk; cb += U * CW * 32) {
@@ -258,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         }
       }
     } else {
-      ptx::pdl_wait_prior_grid();
+      wait_inputs<kHand>(p);
       if (threadIdx.x == 0) stamp(p, 2);
       for (int cb = c_lo; cb < c_hi; cb += CW * 32) {
         const int c = cb + tid;
@@ -524,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
             Cp[m * p.ldc + n] = add_resid<T>(epilogue<T>(v[m], bias, n),
                                              kM1 ? static_cast<const T*>(p.resid) : nullptr, n);
       }
+      signal_tile<kHand>(p);
     } else {
       // push the band sum into rank 0's shared memory (DSMEM); rank 0 adds them in rank order
       const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>((z * MR) * BN + t) * 4u;
@@ -552,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
           }
         }
       }
+      signal_tile<kHand>(p);     // threads 0 .. BN-1 are exactly the CW consumer warps
     }
   }
   if (threadIdx.x == 0) stamp(p, 5);
@@ -589,15 +633,21 @@ struct NextHint {
   int N, K;
 };
 thread_local NextHint g_next = {nullptr, nullptr, 0, 0};
+struct Handover {
+  const unsigned* wait_ctr;
+  unsigned wait_count;
+  unsigned* signal_ctr;
+};
+thread_local Handover g_hand = {nullptr, 0, nullptr};
 
-template <typename T, bool kTrick, bool kM1, int kPro>
+template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
                 int grid, int stages, bool pdl) {
   using C = Cfg<kM1>;
   const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
                       C::xred_bytes(prm.Z) + 16 * stages + 32 +
                       (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
-  auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro>;
+  auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro, kHand>;
   static size_t configured[64] = {0};
   int dev = 0;
   CGQ_CUDA_TRY(cudaGetDevice(&dev));
@@ -636,6 +686,16 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
 template <typename T, bool kTrick>
 int launch_m1(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, const Params& prm,
               int grid, int stages, bool pdl, int pro) {
+  if (prm.wait_ctr != nullptr || prm.signal_ctr != nullptr) {   // tile-granular hand-over variant
+    switch (pro) {
+      case PRO_RMSNORM:
+        return launch_inst<T, kTrick, true, PRO_RMSNORM, true>(a, tmW, tmS, prm, grid, stages, pdl);
+      case PRO_SILU_GATE:
+        return launch_inst<T, kTrick, true, PRO_SILU_GATE, true>(a, tmW, tmS, prm, grid, stages, pdl);
+      default:
+        return launch_inst<T, kTrick, true, PRO_NONE, true>(a, tmW, tmS, prm, grid, stages, pdl);
+    }
+  }
   switch (pro) {
     case PRO_RMSNORM:
       return launch_inst<T, kTrick, true, PRO_RMSNORM>(a, tmW, tmS, prm, grid, stages, pdl);
@@ -693,6 +753,13 @@ int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
   prm.norm_w = fu != nullptr ? fu->norm_w : nullptr;
   prm.eps = fu != nullptr ? fu->eps : 0.f;
   prm.band_units = per_cta;
+  // one-shot hand-over hint (cgq_handover_next); only the fused M == 1 launches take it
+  const Handover hand = g_hand;
+  g_hand = Handover{nullptr, 0, nullptr};
+  const bool use_hand = fu != nullptr && a.M == 1;
+  prm.wait_ctr = use_hand ? hand.wait_ctr : nullptr;
+  prm.wait_count = use_hand ? hand.wait_count : 0;
+  prm.signal_ctr = use_hand ? hand.signal_ctr : nullptr;
   const int pro = fu != nullptr ? fu->prologue : PRO_NONE;
   // one-shot hint: stream the next launch's weights into L2 from this kernel's producers
   const NextHint nh = g_next;
@@ -755,6 +822,11 @@ int launch_w4_gemv(const GemmArgs& a, bool exact) {
 void set_next_w4_hint(const void* w, const void* s, int N, int K) {
   g_next = NextHint{w, s, N, K};
 }
+
+void set_w4_handover(const unsigned* wait_ctr, unsigned wait_count, unsigned* signal_ctr) {
+  g_hand = Handover{wait_ctr, wait_count, signal_ctr};
+}
+int w4_gemv_tiles(int N) { return (N + BN - 1) / BN; }
 
 // M == 1 with a fused prologue (RMSNorm / SiLU-gate on the activation) and residual epilogue.
 int launch_w4_gemv_fused(const GemmArgs& a, const GemvFused& fu) {

@@ -52,8 +52,11 @@ def _is_w4_linear(m) -> bool:
 
 
 class FusedDecodeModel:
-    def __init__(self, model: torch.nn.Module, max_len: int = 1024):
+    def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None):
         cfg = model.config
+        # EXPERIMENTAL (cgq_handover_next): tile-granular hand-over between consecutive
+        # dequant-matmuls instead of griddepcontrol.wait; off unless asked for (argument or CGQ_HANDOVER=1)
+        self.handover = bool(int(os.environ.get("CGQ_HANDOVER", "0") or 0)) if handover is None else bool(handover)
         self.model = model
         self.cfg = cfg
         self.max_len = int(min(max_len, cfg.max_sequence_length - 1))   # row max_len of freqs_cis_cache is read
@@ -100,6 +103,8 @@ class FusedDecodeModel:
         self.ao = z(DH * NH)
         self.u = z(2 * cfg.inner_hidden_size)
         self.logits = z(1, 1, cfg.vocab_size)
+        # hand-over counters: one 128-byte line per producing launch (o_proj, w_in, w_out of every layer)
+        self.ctr = z(3 * cfg.num_layers, 32, dtype=torch.int32)
         # the reference's past_key_values layout (n_batch, n_past, n_groups, 1, d_head), model.py:347-349
         self.kv = tuple((z(1, self.max_len, NG, 1, DH), z(1, self.max_len, NG, 1, DH)) for _ in range(cfg.num_layers))
         self.freqs = self.model.freqs_cis_cache
@@ -109,8 +114,15 @@ class FusedDecodeModel:
         self._ready = True
 
     # ---------------------------------------------------------------- the step, as C-ABI calls
-    def _gemv(self, lib, stream, lin, a, out, prologue=PRO_NONE, norm=None, resid=None, nxt=None):
+    def _gemv(self, lib, stream, lin, a, out, prologue=PRO_NONE, norm=None, resid=None, nxt=None,
+              wait=None, signal=None):
         k2, n = lin.weight.shape
+        if self.handover and (wait is not None or signal is not None):
+            # wait = (counter row, producing linear): poll until all of ITS output tiles are announced
+            _lib.check(lib.cgq_handover_next(
+                None if wait is None else self.ctr[wait[0]].data_ptr(),
+                0 if wait is None else lib.cgq_w4_gemv_tiles(wait[1].weight.shape[1]),
+                None if signal is None else self.ctr[signal].data_ptr()))
         if nxt is not None and self.hints:   # experimental L2 prefetch of the NEXT linear's weights (CGQ_PF_MB)
             _lib.check(lib.cgq_prefetch_next_w4(nxt.weight.data_ptr(), nxt.weight_scale.data_ptr(),
                                                 nxt.weight.shape[1], nxt.weight.shape[0] * 2))
@@ -131,18 +143,27 @@ class FusedDecodeModel:
             self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
             emb.weight.shape[0] * 2, emb.weight.shape[1], 32, self.code, self.state.data_ptr(), stream))
         firsts = [layer.attn.qkv_proj for layer in m.layers][1:] + [m.lm_head]
-        for layer, (kc, vc), nxt in zip(m.layers, self.kv, firsts):
+        if self.handover:
+            self.ctr.zero_()
+        prev_out = None          # (counter row, linear) of the previous layer's w_out
+        for i, (layer, (kc, vc), nxt) in enumerate(zip(m.layers, self.kv, firsts)):
+            # hand-over schedule: o_proj -> w_in -> w_out -> next qkv / lm_head by tile counters; qkv -> attention
+            # -> o_proj stay on griddepcontrol.wait (hazards on x / qkv / ao / u: DESIGN.md §6.1a)
             self._gemv(lib, stream, layer.attn.qkv_proj, self.x, self.qkv, PRO_RMSNORM, layer.attn_ln,
-                       nxt=layer.attn.o_proj)
+                       nxt=layer.attn.o_proj, wait=prev_out)
             _lib.check(lib.cgq_decode_attention(
                 self.qkv.data_ptr(), self.freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.ao.data_ptr(),
                 self.state.data_ptr(), cfg.num_attention_heads, cfg.num_multi_query_groups,
                 cfg.head_hidden_size, self.max_len, self.code, stream))
-            self._gemv(lib, stream, layer.attn.o_proj, self.ao, self.x, resid=self.x, nxt=layer.ffn.w_in)
-            self._gemv(lib, stream, layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln, nxt=layer.ffn.w_out)
-            self._gemv(lib, stream, layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x, nxt=nxt)
+            self._gemv(lib, stream, layer.attn.o_proj, self.ao, self.x, resid=self.x, nxt=layer.ffn.w_in,
+                       signal=3 * i)
+            self._gemv(lib, stream, layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln, nxt=layer.ffn.w_out,
+                       wait=(3 * i, layer.attn.o_proj), signal=3 * i + 1)
+            self._gemv(lib, stream, layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x, nxt=nxt,
+                       wait=(3 * i + 1, layer.ffn.w_in), signal=3 * i + 2)
+            prev_out = (3 * i + 2, layer.ffn.w_out)
         self._gemv(lib, stream, m.lm_head, self.x, self.logits, PRO_RMSNORM, m.final_ln,
-                   nxt=m.layers[0].attn.qkv_proj)     # the next token's first linear
+                   nxt=m.layers[0].attn.qkv_proj, wait=prev_out)     # the next token's first linear
 
     def launches_per_step(self) -> int:
         return 5 * self.cfg.num_layers + 2

@@ -161,6 +161,23 @@ int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void* scale, co
 int cgq_prefetch_next_w4(const uint8_t* Wq, const void* scale, int N, int K);
 
 /*
+ * EXPERIMENTAL one-shot hint (no reference counterpart): tile-granular hand-over between two consecutive
+ * cgq_w4a16_gemv_fused launches instead of the grid-granular `griddepcontrol.wait`.  The NEXT
+ * cgq_w4a16_gemv_fused launch issued by the calling thread
+ *   - `wait_ctr` != NULL: does not wait for the previous grid to drain; its consumers acquire-poll
+ *     *wait_ctr until it reaches `wait_count` (= cgq_w4_gemv_tiles(N) of the launch that produces its input)
+ *     before touching the activation (bounded spin: a lost producer yields wrong numbers, not a hung device);
+ *   - `signal_ctr` != NULL: release-increments *signal_ctr once per stored 128-column output tile.
+ * The caller zeroes the counters on the stream before the first launch that uses them (one counter per
+ * producing launch per step) and keeps launches that reuse an activation buffer apart by a full dependency
+ * (DESIGN.md §6.1a lists the hazards FusedDecodeModel's schedule was checked against).  Either pointer NULL
+ * leaves that side on the default protocol; (NULL, 0, NULL) cancels.  Results are bit-identical.
+ */
+int cgq_handover_next(const uint32_t* wait_ctr, uint32_t wait_count, uint32_t* signal_ctr);
+/* Output tiles (128 columns each) a decode launch with N columns stores -- the count its consumers wait for. */
+int cgq_w4_gemv_tiles(int N);
+
+/*
  * ---- Persistent decode program: a chain of batch-1 int4g32 linears in ONE launch --------------------
  * The same linears as cgq_w4a16_gemv_fused (same arithmetic, bit for bit), executed in the given order by
  * persistent workers: every worker's TMA producer walks the whole chain and keeps its shared-memory ring

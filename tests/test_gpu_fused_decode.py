@@ -4,6 +4,7 @@ behind the model call signature — against oracle/decode_oracle.py on seeded in
 fixture made by the REAL reference model (tests/golden/decode_tiny.npz) and, when the pip-installed
 reference is present (baseline/_ref), against the unmodified reference model running on the same GPU.
 """
+import os
 import sys
 from pathlib import Path
 from types import SimpleNamespace
@@ -240,6 +241,49 @@ def test_fused_decode_matches_unmodified_reference_model(cfg_kwargs):
                 if (top2[0] - top2[1]).item() > 2e-2 * a.abs().max().item():
                     assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
                 tok = a.argmax().reshape(1, 1)
+    finally:
+        uninstall("chatglm_q")
+
+
+@pytest.mark.parametrize("cfg_kwargs", [
+    dict(hidden_size=512, inner_hidden_size=1024, head_hidden_size=64, num_multi_query_groups=2, num_attention_heads=8,
+         num_layers=3, vocab_size=1024, max_sequence_length=256),
+    dict(hidden_size=4096, inner_hidden_size=13696, head_hidden_size=128, num_multi_query_groups=2,
+         num_attention_heads=32, num_layers=3, vocab_size=65024, max_sequence_length=512),   # ChatGLM2-6B layer shapes
+])
+@pytest.mark.skipif(os.environ.get("CGQ_TEST_HANDOVER", "0") != "1",
+                    reason="experimental protocol, not yet measured on a B200: set CGQ_TEST_HANDOVER=1")
+def test_fused_step_tile_handover_bit_identical(cfg_kwargs):
+    """EXPERIMENTAL hand-over protocol (cgq_handover_next): o_proj -> w_in -> w_out -> next qkv / lm_head wait on
+    per-tile counters instead of griddepcontrol.wait.  Same kernels, same arithmetic: logits and KV caches of 30
+    replayed steps must equal the default protocol's bit for bit."""
+    from chatglm_q_b200.install import install, uninstall
+
+    model = _random_ref_model(cfg_kwargs)
+    install("chatglm_q")
+    try:
+        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
+        plain = FusedDecodeModel(model, max_len=64, handover=False)
+        hand = FusedDecodeModel(model, max_len=64, handover=True)
+        with torch.no_grad():
+            _, lg_p, kv_p = plain(input_ids=prompt, past_key_values=None)
+            _, lg_h, kv_h = hand(input_ids=prompt, past_key_values=None)
+            tok = lg_p[0, -1].argmax().reshape(1, 1)
+            for step in range(30):
+                _, lg_p, kv_p = plain(input_ids=tok, past_key_values=kv_p)
+                _, lg_h, kv_h = hand(input_ids=tok, past_key_values=kv_h)
+                assert torch.equal(lg_p, lg_h), f"step {step}: logits differ under the hand-over protocol"
+                tok = lg_p[0, -1].argmax().reshape(1, 1)
+            torch.cuda.synchronize()
+            assert hand.graph is not None and plain.graph is not None
+            for (kp, vp), (kh, vh) in zip(plain.kv, hand.kv):
+                assert torch.equal(kp, kh) and torch.equal(vp, vh)
+            # every producing launch announced exactly its tiles in the last replay
+            want = []
+            for layer in model.layers:
+                want += [(layer.attn.o_proj.weight.shape[1] + 127) // 128, (layer.ffn.w_in.weight.shape[1] + 127) // 128,
+                         (layer.ffn.w_out.weight.shape[1] + 127) // 128]
+            assert hand.ctr[:, 0].cpu().tolist() == want
     finally:
         uninstall("chatglm_q")
 
