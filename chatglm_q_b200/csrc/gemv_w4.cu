@@ -88,6 +88,7 @@ struct Params {
   const unsigned* wait_ctr;
   unsigned wait_count;
   unsigned* signal_ctr;
+  unsigned hand_mode, hand_sleep;   // polling variant (CGQ_HAND_MODE bits, CGQ_HAND_SLEEP ns)
 };
 constexpr int kPfPiece = 16384;
 
@@ -138,11 +139,26 @@ template <bool kHand>
 __device__ __forceinline__ void wait_inputs(const Params& p) {
   if constexpr (kHand) {
     if (p.wait_ctr != nullptr) {
-      if ((threadIdx.x & 31) == 0) {
+      const bool one_poller = (p.hand_mode & 1) != 0;     // thread 0 polls for the CTA, else lane 0 of every warp
+      const bool relaxed = (p.hand_mode & 2) != 0;        // relaxed polls + one acquire at the end
+      if (one_poller ? threadIdx.x == 0 : (threadIdx.x & 31) == 0) {
         unsigned spins = 0;
-        while (ld_acquire_gpu(p.wait_ctr) < p.wait_count && ++spins < (1u << 15)) __nanosleep(20);   // <= ~25 ms
+        if (relaxed) {
+          unsigned v;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_ctr) : "memory");
+            if (v >= p.wait_count) break;
+            __nanosleep(p.hand_sleep);
+          } while (++spins < (1u << 15));
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        } else {
+          while (ld_acquire_gpu(p.wait_ctr) < p.wait_count && ++spins < (1u << 15)) __nanosleep(p.hand_sleep);   // <= ~25 ms
+        }
       }
-      __syncwarp();
+      if (one_poller)
+        ptx::named_bar_sync(1, CW * 32);
+      else
+        __syncwarp();
       return;
     }
   }
@@ -760,6 +776,9 @@ int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
   prm.wait_ctr = use_hand ? hand.wait_ctr : nullptr;
   prm.wait_count = use_hand ? hand.wait_count : 0;
   prm.signal_ctr = use_hand ? hand.signal_ctr : nullptr;
+  static const int hand_mode = env_int("CGQ_HAND_MODE", 0, 0, 3), hand_sleep = env_int("CGQ_HAND_SLEEP", 20, 0, 2000);
+  prm.hand_mode = static_cast<unsigned>(hand_mode);
+  prm.hand_sleep = static_cast<unsigned>(hand_sleep);
   const int pro = fu != nullptr ? fu->prologue : PRO_NONE;
   // one-shot hint: stream the next launch's weights into L2 from this kernel's producers
   const NextHint nh = g_next;

@@ -15,16 +15,19 @@
 //
 // One CTA of 1024 threads (the row is 127 KB and comes from L2 where lm_head just wrote it; the work is
 // ~200 K integer operations -- latency, not bandwidth):
-//   P0  stage the row into shared memory as order-preserving keys (16-byte loads);
-//   P1  per-warp private 256-bin histograms of the high byte.  Lanes with the same digit are merged with
-//       match.any before the shared-memory atomic (logits share a handful of exponents: un-merged atomics
-//       would serialise 32-way); running maximum;
-//   P2  the same for the low byte of the elements inside the threshold bin -> threshold key t, number of
-//       keys above it, and (from the private histograms) how many ties every warp holds;
-//   P3  collect key > t (any order) and the first `need` ties in index order (ballot ranks on top of the
-//       per-warp tie prefix), accumulate sum(exp(v - vmax));
-//   P4  rank the <= 1024 candidates by counting (key desc, index asc), top-p mask on a chunked warp scan,
-//       renormalise, argmax(p / q).
+//   P0  stage the row into shared memory as order-preserving keys (16-byte loads); every thread takes the
+//       maximum of the 64 elements it owns;
+//   F1  FAST PATH: the k-th largest of the 1024 thread maxima, tau, is a lower bound of the k-th largest
+//       element (k threads hold an element >= tau), and for k << 1024 barely more than k elements reach it.
+//       tau comes from an exact two-digit radix select over the 1024 maxima (per-warp private histograms,
+//       lanes with the same digit merged with match.any before the shared-memory atomic);
+//   F2  one scan: sum(exp(v - vmax)) and every element >= tau into the candidate list (ballot-aggregated);
+//   S   SLOW PATH, only if more than 1024 elements reach tau (massive ties, top_k near 1024): the same radix
+//       select over ALL elements (P1 high byte, P2 low byte inside the threshold bin -> threshold key t and
+//       the per-warp tie counts, P3 collect key > t in any order and the first `need` ties in index order).
+//       match.any costs ~100 cycles: 8 000 of them are 60 us, which is why this is not the common path;
+//   P4  rank the <= 1024 candidates by counting (key desc, index asc), keep ranks < k, top-p mask on a
+//       chunked warp scan, renormalise, argmax(p / q).
 #include "common.cuh"
 
 namespace cgq {
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
   int* sidx = reinterpret_cast<int*>(sp + kMaxTopK);                          // [kMaxTopK] sorted indices
   float* redf = reinterpret_cast<float*>(sidx + kMaxTopK);                    // [kWarps]
   uint32_t* redu = reinterpret_cast<uint32_t*>(redf + kWarps);                // [kWarps]
-  uint32_t* sel = redu + kWarps;                                              // [8] bin / above per pass, counters
+  uint32_t* sel = redu + kWarps;                                              // [16] bin / above per pass, counters
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = p.V, k = p.k;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
       k16[i] = static_cast<uint16_t>(kk);
     }
     for (int i = tid; i < kWarps * 256; i += kThreads) hist[i] = 0;
-    if (tid < 8) sel[tid] = 0;
+    if (tid < 16) sel[tid] = 0;
   }
   __syncthreads();
 
@@ -144,120 +147,181 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
   const uint32_t* wkeys = keys32 + (e_base >> 1);
   uint32_t* myhist = hist + warp * 256;
 
-  // ---- P1: high-byte histogram + maximum key
-  uint32_t kmax = 0;
+  // ---- maximum of the elements this thread owns (invalid / padding elements count as key 0)
+  uint32_t tmax = 0;
   for (int s = 0; s < steps; ++s) {
     const uint32_t kk = wkeys[s * 32 + lane];
     const int e0 = e_base + s * 64 + 2 * lane;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t key = (kk >> (16 * h)) & 0xffffu;
-      const bool valid = e0 + h < V;
-      const uint32_t d = valid ? (key >> 8) : 256u;
-      const uint32_t m = __match_any_sync(kFull, d);
-      if (valid && (m & lt) == 0) atomicAdd(&myhist[d], __popc(m));
-      if (valid) kmax = max(kmax, key);
-    }
+    if (e0 < V) tmax = max(tmax, kk & 0xffffu);
+    if (e0 + 1 < V) tmax = max(tmax, kk >> 16);
   }
-  kmax = __reduce_max_sync(kFull, kmax);
-  if (lane == 0) redu[warp] = kmax;
-  __syncthreads();
-  if (tid < 256) {
-    uint32_t t = 0;
-#pragma unroll 8
-    for (int w = 0; w < kWarps; ++w) t += hist[w * 256 + tid];
-    tot[tid] = t;
+  {
+    const uint32_t wmax = __reduce_max_sync(kFull, tmax);
+    if (lane == 0) redu[warp] = wmax;
   }
-  __syncthreads();
-  if (warp == 0) select_bin(tot, static_cast<uint32_t>(k), lane, sel);
-  for (int i = tid; i < kWarps * 256; i += kThreads) hist[i] = 0;
-  __syncthreads();
-  const uint32_t b1 = sel[0], above1 = sel[1];
 
-  // ---- P2: low-byte histogram inside bin b1
-  for (int s = 0; s < steps; ++s) {
-    const uint32_t kk = wkeys[s * 32 + lane];
-    const int e0 = e_base + s * 64 + 2 * lane;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t key = (kk >> (16 * h)) & 0xffffu;
-      const bool act = e0 + h < V && (key >> 8) == b1;
-      const uint32_t d = act ? (key & 0xffu) : 256u;
-      const uint32_t m = __match_any_sync(kFull, d);
-      if (act && (m & lt) == 0) atomicAdd(&myhist[d], __popc(m));
-    }
-  }
-  __syncthreads();
-  if (tid < 256) {
-    uint32_t t = 0;
+  // one 8-bit digit pass of the radix select over the 1024 thread maxima
+  auto tmax_pass = [&](bool act, uint32_t digit, uint32_t kk, uint32_t* out) {
+    const uint32_t d = act ? digit : 256u;
+    const uint32_t m = __match_any_sync(kFull, d);
+    if (act && (m & lt) == 0) atomicAdd(&myhist[d], __popc(m));
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t t = 0;
 #pragma unroll 8
-    for (int w = 0; w < kWarps; ++w) t += hist[w * 256 + tid];
-    tot[tid] = t;
-  }
-  __syncthreads();
-  if (warp == 0) select_bin(tot, static_cast<uint32_t>(k) - above1, lane, sel + 2);
-  __syncthreads();
-  const uint32_t b2 = sel[2];
-  const uint32_t tkey = (b1 << 8) | b2;
-  const uint32_t c_gt = above1 + sel[3];                  // keys strictly above the threshold (< k)
-  const uint32_t need = static_cast<uint32_t>(k) - c_gt;  // ties taken, in index order (>= 1)
-  // ties held by the warps before this one
-  uint32_t tie_rank = lane < warp ? hist[lane * 256 + b2] : 0u;
-  tie_rank = __reduce_add_sync(kFull, tie_rank);
+      for (int w = 0; w < kWarps; ++w) t += hist[w * 256 + tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (warp == 0) select_bin(tot, kk, lane, out);
+    for (int i = tid; i < kWarps * 256; i += kThreads) hist[i] = 0;
+    __syncthreads();
+  };
+  // ---- F1: tau = k-th largest thread maximum
+  tmax_pass(true, tmax >> 8, static_cast<uint32_t>(k), sel + 8);
+  const uint32_t ta = sel[8];
+  tmax_pass((tmax >> 8) == ta, tmax & 0xffu, static_cast<uint32_t>(k) - sel[9], sel + 10);
+  const uint32_t tau = (ta << 8) | sel[10];
   uint32_t gmax = redu[lane];
   gmax = __reduce_max_sync(kFull, gmax);
   const float vmax = key_to_float<T>(gmax) * p.inv_temp;
 
-  // ---- P3: collect the candidates, sum of exponentials
+  // ---- F2: sum of exponentials, candidates = every element >= tau
   float se = 0.f;
   for (int s = 0; s < steps; ++s) {
     const uint32_t kk = wkeys[s * 32 + lane];
     const int e0 = e_base + s * 64 + 2 * lane;
-    bool tie[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t key = (kk >> (16 * h)) & 0xffffu;
       const bool valid = e0 + h < V;
       if (valid) se += expf(key_to_float<T>(key) * p.inv_temp - vmax);
-      const bool gt = valid && key > tkey;
-      tie[h] = valid && key == tkey;
-      const uint32_t bg = __ballot_sync(kFull, gt);
-      if (bg != 0) {
+      const bool cand = valid && key >= tau;
+      const uint32_t bc = __ballot_sync(kFull, cand);
+      if (bc != 0) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&sel[4], __popc(bg));
+        if (lane == 0) base = atomicAdd(&sel[12], __popc(bc));
         base = __shfl_sync(kFull, base, 0);
-        if (gt)
-          comp[base + __popc(bg & lt)] =
-              (static_cast<unsigned long long>(key) << 32) | (0xffffffffu - static_cast<uint32_t>(e0 + h));
+        const uint32_t slot = base + __popc(bc & lt);
+        if (cand && slot < static_cast<uint32_t>(kMaxTopK))
+          comp[slot] = (static_cast<unsigned long long>(key) << 32) | (0xffffffffu - static_cast<uint32_t>(e0 + h));
       }
-    }
-    const uint32_t t0 = __ballot_sync(kFull, tie[0]), t1 = __ballot_sync(kFull, tie[1]);
-    if ((t0 | t1) != 0) {
-      const uint32_t r0 = tie_rank + __popc(t0 & lt) + __popc(t1 & lt);
-      const uint32_t r1 = r0 + (tie[0] ? 1u : 0u);
-      if (tie[0] && r0 < need)
-        comp[c_gt + r0] = (static_cast<unsigned long long>(tkey) << 32) | (0xffffffffu - static_cast<uint32_t>(e0));
-      if (tie[1] && r1 < need)
-        comp[c_gt + r1] = (static_cast<unsigned long long>(tkey) << 32) | (0xffffffffu - static_cast<uint32_t>(e0 + 1));
-      tie_rank += __popc(t0) + __popc(t1);
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(kFull, se, o);
   if (lane == 0) redf[warp] = se;
   __syncthreads();
+  int n_cand = static_cast<int>(sel[12]);       // >= k by construction of tau
 
-  // ---- P4: order the k candidates (key descending, index ascending), probabilities
+  if (n_cand > kMaxTopK) {
+    // ---- S: exact radix select over all elements (block-uniform branch)
+    // P1: high-byte histogram
+    for (int s = 0; s < steps; ++s) {
+      const uint32_t kk = wkeys[s * 32 + lane];
+      const int e0 = e_base + s * 64 + 2 * lane;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t key = (kk >> (16 * h)) & 0xffffu;
+        const bool valid = e0 + h < V;
+        const uint32_t d = valid ? (key >> 8) : 256u;
+        const uint32_t m = __match_any_sync(kFull, d);
+        if (valid && (m & lt) == 0) atomicAdd(&myhist[d], __popc(m));
+      }
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t t = 0;
+#pragma unroll 8
+      for (int w = 0; w < kWarps; ++w) t += hist[w * 256 + tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (warp == 0) select_bin(tot, static_cast<uint32_t>(k), lane, sel);
+    for (int i = tid; i < kWarps * 256; i += kThreads) hist[i] = 0;
+    __syncthreads();
+    const uint32_t b1 = sel[0], above1 = sel[1];
+
+    // P2: low-byte histogram inside bin b1
+    for (int s = 0; s < steps; ++s) {
+      const uint32_t kk = wkeys[s * 32 + lane];
+      const int e0 = e_base + s * 64 + 2 * lane;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t key = (kk >> (16 * h)) & 0xffffu;
+        const bool act = e0 + h < V && (key >> 8) == b1;
+        const uint32_t d = act ? (key & 0xffu) : 256u;
+        const uint32_t m = __match_any_sync(kFull, d);
+        if (act && (m & lt) == 0) atomicAdd(&myhist[d], __popc(m));
+      }
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t t = 0;
+#pragma unroll 8
+      for (int w = 0; w < kWarps; ++w) t += hist[w * 256 + tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    if (warp == 0) select_bin(tot, static_cast<uint32_t>(k) - above1, lane, sel + 2);
+    __syncthreads();
+    const uint32_t b2 = sel[2];
+    const uint32_t tkey = (b1 << 8) | b2;
+    const uint32_t c_gt = above1 + sel[3];                  // keys strictly above the threshold (< k)
+    const uint32_t need = static_cast<uint32_t>(k) - c_gt;  // ties taken, in index order (>= 1)
+    // ties held by the warps before this one
+    uint32_t tie_rank = lane < warp ? hist[lane * 256 + b2] : 0u;
+    tie_rank = __reduce_add_sync(kFull, tie_rank);
+
+    // P3: collect key > t (any order) and the first `need` ties in index order
+    for (int s = 0; s < steps; ++s) {
+      const uint32_t kk = wkeys[s * 32 + lane];
+      const int e0 = e_base + s * 64 + 2 * lane;
+      bool tie[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t key = (kk >> (16 * h)) & 0xffffu;
+        const bool valid = e0 + h < V;
+        const bool gt = valid && key > tkey;
+        tie[h] = valid && key == tkey;
+        const uint32_t bg = __ballot_sync(kFull, gt);
+        if (bg != 0) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sel[4], __popc(bg));
+          base = __shfl_sync(kFull, base, 0);
+          if (gt)
+            comp[base + __popc(bg & lt)] =
+                (static_cast<unsigned long long>(key) << 32) | (0xffffffffu - static_cast<uint32_t>(e0 + h));
+        }
+      }
+      const uint32_t t0 = __ballot_sync(kFull, tie[0]), t1 = __ballot_sync(kFull, tie[1]);
+      if ((t0 | t1) != 0) {
+        const uint32_t r0 = tie_rank + __popc(t0 & lt) + __popc(t1 & lt);
+        const uint32_t r1 = r0 + (tie[0] ? 1u : 0u);
+        if (tie[0] && r0 < need)
+          comp[c_gt + r0] = (static_cast<unsigned long long>(tkey) << 32) | (0xffffffffu - static_cast<uint32_t>(e0));
+        if (tie[1] && r1 < need)
+          comp[c_gt + r1] = (static_cast<unsigned long long>(tkey) << 32) | (0xffffffffu - static_cast<uint32_t>(e0 + 1));
+        tie_rank += __popc(t0) + __popc(t1);
+      }
+    }
+    n_cand = k;
+    __syncthreads();
+  }
+
+  // ---- P4: order the candidates (key descending, index ascending), keep the first k, probabilities
   float sumexp = redf[lane];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sumexp += __shfl_xor_sync(kFull, sumexp, o);
-  if (tid < k) {
+  if (tid < n_cand) {
     const unsigned long long mine = comp[tid];
     int r = 0;
-    for (int j = 0; j < k; ++j) r += comp[j] > mine ? 1 : 0;
-    const uint32_t key = static_cast<uint32_t>(mine >> 32);
-    sp[r] = expf(key_to_float<T>(key) * p.inv_temp - vmax) / sumexp;
-    sidx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(mine));
+    for (int j = 0; j < n_cand; ++j) r += comp[j] > mine ? 1 : 0;
+    if (r < k) {
+      const uint32_t key = static_cast<uint32_t>(mine >> 32);
+      sp[r] = expf(key_to_float<T>(key) * p.inv_temp - vmax) / sumexp;
+      sidx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(mine));
+    }
   }
   __syncthreads();
   if (warp != 0) return;
@@ -312,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
 
 size_t sample_smem_bytes(int vpad) {
   return static_cast<size_t>(vpad) * 2 + sizeof(uint32_t) * (kWarps * 256 + 256) +
-         kMaxTopK * (sizeof(unsigned long long) + sizeof(float) + sizeof(int)) + kWarps * 8 + 8 * 4;
+         kMaxTopK * (sizeof(unsigned long long) + sizeof(float) + sizeof(int)) + kWarps * 8 + 16 * 4;
 }
 
 template <typename T>

@@ -57,6 +57,8 @@ class FusedDecodeModel:
         # EXPERIMENTAL (cgq_handover_next): tile-granular hand-over between consecutive
         # dequant-matmuls instead of griddepcontrol.wait; off unless asked for (argument or CGQ_HANDOVER=1)
         self.handover = bool(int(os.environ.get("CGQ_HANDOVER", "0") or 0)) if handover is None else bool(handover)
+        # which hand-overs take the counters: 1 o_proj->w_in, 2 w_in->w_out, 4 w_out->next qkv / lm_head
+        self.hand_mask = int(os.environ.get("CGQ_HAND_MASK", "7") or 7)
         self.model = model
         self.cfg = cfg
         self.max_len = int(min(max_len, cfg.max_sequence_length - 1))   # row max_len of freqs_cis_cache is read
@@ -150,20 +152,22 @@ class FusedDecodeModel:
             # hand-over schedule: o_proj -> w_in -> w_out -> next qkv / lm_head by tile counters; qkv -> attention
             # -> o_proj stay on griddepcontrol.wait (hazards on x / qkv / ao / u: DESIGN.md §6.1a)
             self._gemv(lib, stream, layer.attn.qkv_proj, self.x, self.qkv, PRO_RMSNORM, layer.attn_ln,
-                       nxt=layer.attn.o_proj, wait=prev_out)
+                       nxt=layer.attn.o_proj, wait=prev_out if self.hand_mask & 4 else None)
             _lib.check(lib.cgq_decode_attention(
                 self.qkv.data_ptr(), self.freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.ao.data_ptr(),
                 self.state.data_ptr(), cfg.num_attention_heads, cfg.num_multi_query_groups,
                 cfg.head_hidden_size, self.max_len, self.code, stream))
+            hm = self.hand_mask
             self._gemv(lib, stream, layer.attn.o_proj, self.ao, self.x, resid=self.x, nxt=layer.ffn.w_in,
-                       signal=3 * i)
+                       signal=3 * i if hm & 1 else None)
             self._gemv(lib, stream, layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln, nxt=layer.ffn.w_out,
-                       wait=(3 * i, layer.attn.o_proj), signal=3 * i + 1)
+                       wait=(3 * i, layer.attn.o_proj) if hm & 1 else None, signal=3 * i + 1 if hm & 2 else None)
             self._gemv(lib, stream, layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x, nxt=nxt,
-                       wait=(3 * i + 1, layer.ffn.w_in), signal=3 * i + 2)
+                       wait=(3 * i + 1, layer.ffn.w_in) if hm & 2 else None, signal=3 * i + 2 if hm & 4 else None)
             prev_out = (3 * i + 2, layer.ffn.w_out)
         self._gemv(lib, stream, m.lm_head, self.x, self.logits, PRO_RMSNORM, m.final_ln,
-                   nxt=m.layers[0].attn.qkv_proj, wait=prev_out)     # the next token's first linear
+                   nxt=m.layers[0].attn.qkv_proj,     # the next token's first linear
+                   wait=prev_out if self.hand_mask & 4 else None)
 
     def launches_per_step(self) -> int:
         return 5 * self.cfg.num_layers + 2

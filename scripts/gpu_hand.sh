@@ -1,5 +1,7 @@
 #!/bin/bash
-# experimental tile-granular hand-over: bit-identity test + timing against the default protocol
+# experimental tile-granular hand-over: which polling variant / which hand-overs cost what
 out=gpurun_out/${1:-hand}; mkdir -p $out
-CGQ_TEST_HANDOVER=1 timeout 400 python -m pytest tests/test_gpu_fused_decode.py -q -m gpu -k "handover" > $out/pytest.log 2>&1; echo "pytest rc=$?"; tail -12 $out/pytest.log
-timeout 240 python scripts/time_fused_step.py 2>&1 | tee $out/time.log | tail -6
+for cfg in "0 20 7" "1 20 7" "3 20 7" "3 200 7" "3 20 1" "3 20 2" "3 20 4"; do
+  set -- $cfg
+  CGQ_HAND_MODE=$1 CGQ_HAND_SLEEP=$2 CGQ_HAND_MASK=$3 timeout 120 python scripts/time_fused_step.py 2>&1 | grep "fused step" | tee -a $out/time.log
+done

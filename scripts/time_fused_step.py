@@ -1,5 +1,6 @@
 """Device time of the fused decode step of the full-size random ChatGLM2-6B int4g32 model, default protocol
 against the experimental tile-granular hand-over (CGQ_HANDOVER / FusedDecodeModel(handover=True))."""
+import os
 import sys
 from pathlib import Path
 
@@ -18,7 +19,7 @@ install("chatglm_q")
 cfg, model = bench.build_ref_int4_model(torch, dev)
 prompt = torch.tensor([bench.StubTokenizer(32).encode("x")], device=dev)
 ref_logits = None
-for hand in (False, True, False, True):
+for hand in (False, True):
     fm = FusedDecodeModel(model, max_len=256, handover=hand)
     with torch.no_grad():
         _, lg, kv = fm(input_ids=prompt, past_key_values=None)
@@ -42,5 +43,6 @@ for hand in (False, True, False, True):
         fm.graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    print(f"fused step handover={hand}: {e0.elapsed_time(e1) * 1e3 / reps:.1f} us/token, logits identical to default: {same}")
+    print(f"[mode={os.environ.get('CGQ_HAND_MODE', '0')} sleep={os.environ.get('CGQ_HAND_SLEEP', '20')} mask={os.environ.get('CGQ_HAND_MASK', '7')}] "
+          f"fused step handover={hand}: {e0.elapsed_time(e1) * 1e3 / reps:.1f} us/token, logits identical to default: {same}")
     del fm
