@@ -361,11 +361,22 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     fused_ref_sampler, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
     # the sampler is a module global of the reference too (decoder.py:12, resolved at :85): rebind it to the
     # one-launch cgq_top_p_sample (same signature, same token for the same seed) -- the headline configuration
+    from chatglm_q_b200.install import uninstall
     install("chatglm_q", sampler=True)
     try:
-        fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+        fused_sync, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
     finally:
-        from chatglm_q_b200.install import uninstall
+        uninstall("chatglm_q")
+        install("chatglm_q")
+    # headline: the sampler bound to the model starts the NEXT step from the device-resident token, so the decoder's
+    # host round trip overlaps it (exact: the token is checked on the host, a mismatch takes the step back).  The
+    # decoder gets device=None: it then hands the CPU token ids to the wrapper, which copies them itself.
+    del fused_model
+    fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32, speculate=True)
+    install("chatglm_q", sampler=fused_model.sampler())
+    try:
+        fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=None, time_log=False))
+    finally:
         uninstall("chatglm_q")
         install("chatglm_q")
     # device time of the fused step alone (graph replays between CUDA events; the KV window is rewound so
@@ -394,10 +405,15 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
                    f"PDL-chained); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after the first / "
                    f"their summed wall time (each step: H2D token id, graph replay, top-p sampling by cgq_top_p_sample "
                    f"bound to the decoder's top_p_sampling global -- 2 launches instead of the reference's ~15 torch kernels "
-                   f"and multinomial's host sync --, .item() D2H)",
+                   f"and multinomial's host sync --, D2H of the token; the next step's replay is issued from the "
+                   f"device-resident token right after the sampling kernel and verified against the id the decoder "
+                   f"passes back)",
             "prefill_s": prefill_s, "tokens": n_tok,
             "fused_step_reference_sampler": {"value": fused_ref_sampler,
                                              "how": "same fused step, the reference's own torch top_p_sampling"},
+            "fused_step_cgq_sampler_no_overlap": {"value": fused_sync,
+                                                  "how": "same fused step, cgq_top_p_sample, next step launched only "
+                                                         "when the decoder calls the model again"},
             "fused_step_device_us": dev_us, "fused_step_launches": launches,
             "graphed_reference_forward": {"value": graphed, "prefill_s": graphed_prefill,
                                           "how": "same decoder, unmodified model forward captured in one CUDA graph "

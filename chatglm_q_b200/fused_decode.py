@@ -52,8 +52,17 @@ def _is_w4_linear(m) -> bool:
 
 
 class FusedDecodeModel:
-    def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None):
+    def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None,
+                 speculate: bool = False):
         cfg = model.config
+        # speculate=True: `self.sampler()` (bound to the decoder's top_p_sampling) starts the NEXT step from the
+        # device-resident token right after the sampling kernel, so the decoder's host round trip (.item(), Python,
+        # the H2D copy of the token id) overlaps the step instead of idling the GPU.  Exact: the next call's token is
+        # checked on the host and a mismatch takes the step back.  Needs CPU `input_ids` (ChatGLMDecoder(device=None)).
+        self.speculate = bool(speculate)
+        self._spec = False
+        self._spec_token = None
+        self._host_ids = False
         # EXPERIMENTAL (cgq_handover_next): tile-granular hand-over between consecutive
         # dequant-matmuls instead of griddepcontrol.wait; off unless asked for (argument or CGQ_HANDOVER=1)
         self.handover = bool(int(os.environ.get("CGQ_HANDOVER", "0") or 0)) if handover is None else bool(handover)
@@ -105,6 +114,10 @@ class FusedDecodeModel:
         self.ao = z(DH * NH)
         self.u = z(2 * cfg.inner_hidden_size)
         self.logits = z(1, 1, cfg.vocab_size)
+        self.tok_dev = z(1, dtype=torch.long)
+        self.tok_host = torch.zeros(1, dtype=torch.long).pin_memory()
+        self.tok_event = torch.cuda.Event()
+        self._spec = False
         # hand-over counters: one 128-byte line per producing launch (o_proj, w_in, w_out of every layer)
         self.ctr = z(3 * cfg.num_layers, 32, dtype=torch.int32)
         # the reference's past_key_values layout (n_batch, n_past, n_groups, 1, d_head), model.py:347-349
@@ -192,23 +205,86 @@ class FusedDecodeModel:
     def __call__(self, input_ids: Tensor = None, past_key_values=None, **kwargs):
         if kwargs or input_ids is None:
             return self.model(input_ids=input_ids, past_key_values=past_key_values, **kwargs)
+        on_host = input_ids.device.type == "cpu"
+        dev = self.model.lm_head.weight.device
         fresh = past_key_values is None or not isinstance(past_key_values, _FusedCache)
         if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
-            loss, logits, kv = self.model(input_ids=input_ids,
+            self._drop_speculation()
+            loss, logits, kv = self.model(input_ids=input_ids.to(dev),
                                           past_key_values=None if fresh else self._export_kv())
-            self._import_kv(kv, input_ids.device)
+            self._import_kv(kv, dev)
             return loss, logits, _FusedCache(self)
+        if self._spec:
+            # a step for the token the sampler produced is already in flight (self.sampler())
+            self._spec = False
+            if on_host and int(input_ids[0, 0]) == self._spec_token:
+                self.n_valid += 1
+                self._host_ids = True
+                return None, self.logits, past_key_values
+            self._drop_speculation(rewind=True)      # another token: take the step back, run the right one
         if self._eager_kv is not None or self.n_valid + 1 > self.max_len:
             if self._eager_kv is None:
                 self._eager_kv = self._export_kv()
-            loss, logits, self._eager_kv = self.model(input_ids=input_ids, past_key_values=self._eager_kv)
+            loss, logits, self._eager_kv = self.model(input_ids=input_ids.to(dev), past_key_values=self._eager_kv)
             return loss, logits, past_key_values
+        self._host_ids = on_host
         self.ids.copy_(input_ids, non_blocking=True)
         if self.graph is None:
             self._capture()
         self.graph.replay()
         self.n_valid += 1
         return None, self.logits, past_key_values
+
+    # ---------------------------------------------------------------- sampler bound to this model (speculation)
+    def _drop_speculation(self, rewind: bool = False):
+        """Forget an in-flight speculative step.  Its KV row (slot n_valid) is overwritten by whatever runs next;
+        the device-side position is put back when the fused step continues from here (`rewind`) — a prefill
+        re-imports the cache and sets it anyway."""
+        if self._spec or rewind:
+            self._spec = False
+            if rewind:
+                self.state.copy_(torch.tensor([self.n_valid, self.n_valid], dtype=torch.int32), non_blocking=False)
+
+    def _can_speculate(self, logits: Tensor) -> bool:
+        return (self.speculate and self._ready and self.graph is not None and self._host_ids
+                and self._eager_kv is None and logits.dim() == 1 and logits.data_ptr() == self.logits.data_ptr()
+                and self.n_valid + 1 <= self.max_len)
+
+    def sampler(self):
+        """A `top_p_sampling(logits, top_k, top_p, temperature)` (chatglm_q/decoder.py:12-27) bound to this model, for
+        `install(package, sampler=model.sampler())`.  On the logits of a fused step it runs cgq_top_p_sample with the
+        token left on the device, copies it to pinned host memory, starts the next step from the device copy and only
+        then waits for the host copy: the GPU does not idle across the decoder's host round trip.  Returns a CPU
+        0-dim int64 tensor in that case (the decoder calls `.item()` on it); anything else goes to ops.top_p_sampling.
+        Same Exp(1) draw as ops.top_p_sampling / torch.multinomial: the same seed gives the same tokens."""
+        from . import ops
+
+        def top_p_sampling(logits: Tensor, top_k=100, top_p=0.8, temperature=1.0):
+            if self._spec and logits.data_ptr() == self.logits.data_ptr():
+                raise RuntimeError("FusedDecodeModel.sampler(): the logits of this step were already sampled and the "
+                                   "next step has been started from that token (one sample per step)")
+            if not self._can_speculate(logits):
+                return ops.top_p_sampling(logits, top_k, top_p, temperature)
+            assert temperature > 0 and top_p >= 0 and top_k >= 1
+            lib = _lib.load()
+            V = logits.shape[-1]
+            k = min(int(top_k), V)
+            with torch.cuda.device(self.device):
+                q = torch.empty((1, k), dtype=torch.float32, device=self.device).exponential_(1)
+                stream = torch.cuda.current_stream().cuda_stream
+                _lib.check(lib.cgq_top_p_sample(logits.data_ptr(), V, self.code, int(top_k), float(top_p),
+                                                float(temperature), q.data_ptr(), self.tok_dev.data_ptr(), None, None,
+                                                stream))
+                self.tok_host.copy_(self.tok_dev, non_blocking=True)
+                self.tok_event.record()
+                self.ids.copy_(self.tok_dev.view(1, 1), non_blocking=True)
+                self.graph.replay()
+                self._spec = True
+                self.tok_event.synchronize()
+            self._spec_token = int(self.tok_host[0])
+            return torch.tensor(self._spec_token, dtype=torch.long)
+
+        return top_p_sampling
 
     # ---------------------------------------------------------------- cache import / export
     def _import_kv(self, kv, device):

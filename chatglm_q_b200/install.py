@@ -13,12 +13,13 @@ from . import ops
 _saved: dict[str, dict[str, object]] = {}
 
 
-def install(package: str = "chatglm_q", sampler: bool = False) -> None:
+def install(package: str = "chatglm_q", sampler=False) -> None:
     """Rebind `<package>.int4.qlinear` / `<package>.int8.qlinear` kernel globals to chatglm_q_b200.
 
     `sampler=True` also rebinds `<package>.decoder.top_p_sampling` (decoder.py:12-27), which
     `ChatGLMDecoder.generate` resolves by global name at call time (decoder.py:85), to the one-launch
-    `ops.top_p_sampling` (same signature, same token for the same torch seed; CUDA fp16 / bf16 logits only)."""
+    `ops.top_p_sampling` (same signature, same token for the same torch seed; CUDA fp16 / bf16 logits only).
+    `sampler=<callable>` binds that callable instead (e.g. `FusedDecodeModel.sampler()`)."""
     q4 = importlib.import_module(f"{package}.int4.qlinear")
     q8 = importlib.import_module(f"{package}.int8.qlinear")
     for mod, impl in ((q4, ops.dynamic_quant_matmul_s4), (q8, ops.dynamic_quant_matmul)):
@@ -34,7 +35,7 @@ def install(package: str = "chatglm_q", sampler: bool = False) -> None:
         dec = importlib.import_module(f"{package}.decoder")
         if dec.__name__ not in _saved:
             _saved[dec.__name__] = {"top_p_sampling": dec.top_p_sampling}
-        dec.top_p_sampling = ops.top_p_sampling
+        dec.top_p_sampling = sampler if callable(sampler) else ops.top_p_sampling
 
 
 def uninstall(package: str = "chatglm_q") -> None:

@@ -288,6 +288,58 @@ def test_fused_step_tile_handover_bit_identical(cfg_kwargs):
         uninstall("chatglm_q")
 
 
+def test_speculative_next_step_is_exact():
+    """FusedDecodeModel(speculate=True) + its sampler(): the next step is started from the device-resident token
+    before the host sees it.  Driven like ChatGLMDecoder.generate with CPU ids (decoder device=None): same seed ->
+    the same tokens and bit-identical logits as the plain fused model with ops.top_p_sampling, across the end of the
+    static KV window; a caller that feeds ANOTHER token gets the step taken back and redone."""
+    from chatglm_q_b200.install import install, uninstall
+
+    cfg_kwargs = dict(hidden_size=512, inner_hidden_size=1024, head_hidden_size=64, num_multi_query_groups=2,
+                      num_attention_heads=8, num_layers=3, vocab_size=1024, max_sequence_length=256)
+    model = _random_ref_model(cfg_kwargs)
+    install("chatglm_q")
+    try:
+        def run(fm, sampler, n, on_host, swap_at=None):
+            torch.manual_seed(11)
+            ids = torch.tensor([[5, 17, 300, 42, 7]])
+            with torch.no_grad():
+                _, lg, kv = fm(input_ids=ids if on_host else ids.to(DEV), past_key_values=None)
+                toks, logs = [], []
+                for i in range(n):
+                    tok = int(sampler(lg[0, -1], 50, 0.9, 1.0).item())
+                    if swap_at is not None and i == swap_at:
+                        tok = (tok + 1) % 1024            # not what was sampled: the speculation must be undone
+                    toks.append(tok)
+                    nxt = torch.tensor([[tok]])
+                    _, lg, kv = fm(input_ids=nxt if on_host else nxt.to(DEV), past_key_values=kv)
+                    logs.append(lg[0, -1].clone())
+            torch.cuda.synchronize()
+            return toks, logs
+
+        for swap in (None, 7):
+            plain = FusedDecodeModel(model, max_len=48)
+            spec = FusedDecodeModel(model, max_len=48, speculate=True)
+            t_a, l_a = run(plain, ops.top_p_sampling, 60, False, swap)      # runs past the 48-row window
+            t_b, l_b = run(spec, spec.sampler(), 60, True, swap)
+            assert t_a == t_b, f"tokens differ (swap={swap})"
+            for i, (a, b) in enumerate(zip(l_a, l_b)):
+                assert torch.equal(a, b), f"step {i}: logits differ under speculation (swap={swap})"
+        # one sample per step: the logits buffer already belongs to the next step
+        spec = FusedDecodeModel(model, max_len=48, speculate=True)
+        samp = spec.sampler()
+        with torch.no_grad():
+            _, lg, kv = spec(input_ids=torch.tensor([[5, 17, 300]]), past_key_values=None)
+            tok = int(samp(lg[0, -1]).item())
+            _, lg, kv = spec(input_ids=torch.tensor([[tok]]), past_key_values=kv)
+            t1 = samp(lg[0, -1])
+            assert t1.device.type == "cpu" and spec._spec
+            with pytest.raises(RuntimeError):
+                samp(lg[0, -1])
+    finally:
+        uninstall("chatglm_q")
+
+
 def test_fused_decode_rejects_unsupported_models():
     w, cfg, _ = load_decode_golden()
     model = _duck_model(w, cfg)
