@@ -362,20 +362,21 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     # the sampler is a module global of the reference too (decoder.py:12, resolved at :85): rebind it to the
     # one-launch cgq_top_p_sample (same signature, same token for the same seed) -- the headline configuration
     from chatglm_q_b200.install import uninstall
+    # headline: every step copies the token id host -> device and reads the sampled token back (8 bytes each way)
     install("chatglm_q", sampler=True)
     try:
-        fused_sync, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
+        fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
     finally:
         uninstall("chatglm_q")
         install("chatglm_q")
-    # headline: the sampler bound to the model starts the NEXT step from the device-resident token, so the decoder's
-    # host round trip overlaps it (exact: the token is checked on the host, a mismatch takes the step back).  The
-    # decoder gets device=None: it then hands the CPU token ids to the wrapper, which copies them itself.
+    # reported beside it: the sampler bound to the model starts the NEXT step from the device-resident token, so the
+    # decoder's host round trip overlaps the step (exact: the id the decoder hands back is checked on the host, a
+    # mismatch takes the step back).  The decoder gets device=None and passes CPU ids; on a hit nothing is copied H2D.
     del fused_model
     fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32, speculate=True)
     install("chatglm_q", sampler=fused_model.sampler())
     try:
-        fused, prefill_s, n_tok = run(ChatGLMDecoder(cfg, fused_model, tok, device=None, time_log=False))
+        fused_spec, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=None, time_log=False))
     finally:
         uninstall("chatglm_q")
         install("chatglm_q")
@@ -405,15 +406,16 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
                    f"PDL-chained); prompt {prompt_len} tok, {n_tok} tok generated, 'gen' tok/s = tokens after the first / "
                    f"their summed wall time (each step: H2D token id, graph replay, top-p sampling by cgq_top_p_sample "
                    f"bound to the decoder's top_p_sampling global -- 2 launches instead of the reference's ~15 torch kernels "
-                   f"and multinomial's host sync --, D2H of the token; the next step's replay is issued from the "
-                   f"device-resident token right after the sampling kernel and verified against the id the decoder "
-                   f"passes back)",
+                   f"and multinomial's host sync --, .item() D2H)",
             "prefill_s": prefill_s, "tokens": n_tok,
             "fused_step_reference_sampler": {"value": fused_ref_sampler,
                                              "how": "same fused step, the reference's own torch top_p_sampling"},
-            "fused_step_cgq_sampler_no_overlap": {"value": fused_sync,
-                                                  "how": "same fused step, cgq_top_p_sample, next step launched only "
-                                                         "when the decoder calls the model again"},
+            "fused_step_speculative_next_step": {"value": fused_spec, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                                                 "how": "FusedDecodeModel(speculate=True).sampler(): the next step's graph "
+                                                        "replay is issued from the device-resident token right after the "
+                                                        "sampling kernel and verified against the CPU id the decoder "
+                                                        "(device=None) hands back; the GPU does not idle across the host "
+                                                        "round trip"},
             "fused_step_device_us": dev_us, "fused_step_launches": launches,
             "graphed_reference_forward": {"value": graphed, "prefill_s": graphed_prefill,
                                           "how": "same decoder, unmodified model forward captured in one CUDA graph "

@@ -5,5 +5,5 @@ timeout 600 python bench.py --no-micro --no-cpu > $out/bench.json 2> $out/bench.
 python - <<'PY'
 import json
 d=json.loads(open("" + __import__("sys").argv[1]).read().strip().splitlines()[-1])
-e=d["e2e"]; print("value", d["value"], "e2e", e["value"], "no-overlap", e["fused_step_cgq_sampler_no_overlap"]["value"], "ref sampler", e["fused_step_reference_sampler"]["value"], "dev_us", e["fused_step_device_us"])
+e=d["e2e"]; print("value", d["value"], "e2e", e["value"], "speculative", e["fused_step_speculative_next_step"]["value"], "ref sampler", e["fused_step_reference_sampler"]["value"], "dev_us", e["fused_step_device_us"])
 PY
