@@ -163,6 +163,11 @@ def test_install_rebinds_reference_globals():
         assert dec.top_p_sampling is ops.top_p_sampling
         install.uninstall(pkg)
         assert dec.top_p_sampling is sentinel
+        bound = lambda logits, top_k=100, top_p=0.8, temperature=1.0: None   # noqa: E731  e.g. FusedDecodeModel.sampler()
+        install.install(pkg, sampler=bound)
+        assert dec.top_p_sampling is bound
+        install.uninstall(pkg)
+        assert dec.top_p_sampling is sentinel
     finally:
         for name in mods:
             sys.modules.pop(name, None)
@@ -205,6 +210,11 @@ def test_fused_decode_wrapper_host_logic():
 
     fused = FusedDecodeModel(model(), max_len=1000)
     assert fused.max_len == 63 and fused.launches_per_step() == 7          # window clipped to the rotary table
+    # opt-in modes are off by default; the bound sampler defers to ops.top_p_sampling unless a fused step is live
+    assert not fused.speculate and not fused.handover and not fused._spec
+    spec = FusedDecodeModel(model(), max_len=32, speculate=True)
+    assert spec.speculate and callable(spec.sampler())
+    assert not spec._can_speculate(torch.zeros(256, dtype=torch.float16))   # nothing captured yet
     assert isinstance(accelerate(model()), FusedDecodeModel)
     for bad in (model(wdtype=torch.int8), model(sdtype=torch.float32), model(head=32)):
         try:
