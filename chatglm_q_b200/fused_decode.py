@@ -53,8 +53,13 @@ def _is_w4_linear(m) -> bool:
 
 class FusedDecodeModel:
     def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None,
-                 speculate: bool = False):
+                 speculate: bool = False, last_logits_only: bool = False):
         cfg = model.config
+        # last_logits_only=True: a prefill (several tokens) computes lm_head for the LAST position only and returns
+        # logits [1, 1, V] -- all ChatGLMDecoder.generate reads is logits[0, -1] (decoder.py:85); at 2 048 tokens that
+        # is 1.09 TFLOP and a 266 MB logits tensor less.  Off by default: the reference returns
+        # every position.
+        self.last_logits_only = bool(last_logits_only)
         # speculate=True: `self.sampler()` (bound to the decoder's top_p_sampling) starts the NEXT step from the
         # device-resident token right after the sampling kernel, so the decoder's host round trip (.item(), Python,
         # the H2D copy of the token id) overlaps the step instead of idling the GPU.  Exact: the next call's token is
@@ -115,8 +120,9 @@ class FusedDecodeModel:
         self.u = z(2 * cfg.inner_hidden_size)
         self.logits = z(1, 1, cfg.vocab_size)
         self.tok_dev = z(1, dtype=torch.long)
-        self.tok_host = torch.zeros(1, dtype=torch.long).pin_memory()
-        self.tok_event = torch.cuda.Event()
+        on_gpu = torch.device(device).type == "cuda"
+        self.tok_host = torch.zeros(1, dtype=torch.long).pin_memory() if on_gpu else torch.zeros(1, dtype=torch.long)
+        self.tok_event = torch.cuda.Event() if on_gpu else None
         self._spec = False
         # hand-over counters: one 128-byte line per producing launch (o_proj, w_in, w_out of every layer)
         self.ctr = z(3 * cfg.num_layers, 32, dtype=torch.int32)
@@ -210,8 +216,9 @@ class FusedDecodeModel:
         fresh = past_key_values is None or not isinstance(past_key_values, _FusedCache)
         if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
             self._drop_speculation()
-            loss, logits, kv = self.model(input_ids=input_ids.to(dev),
-                                          past_key_values=None if fresh else self._export_kv())
+            with self._last_position_head():
+                loss, logits, kv = self.model(input_ids=input_ids.to(dev),
+                                              past_key_values=None if fresh else self._export_kv())
             self._import_kv(kv, dev)
             return loss, logits, _FusedCache(self)
         if self._spec:
@@ -234,6 +241,33 @@ class FusedDecodeModel:
         self.graph.replay()
         self.n_valid += 1
         return None, self.logits, past_key_values
+
+    def _last_position_head(self):
+        """Context manager: while active, `model.lm_head` only sees the last position of its input (the unmodified
+        ChatGLM2Model.forward applies it to every position, model.py:381-382)."""
+        import contextlib
+
+        if not self.last_logits_only or not isinstance(self.model, torch.nn.Module):
+            return contextlib.nullcontext()
+        model, head = self.model, self.model.lm_head
+
+        class _LastRow(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.inner = head
+
+            def forward(self, x):
+                return self.inner(x[:, -1:, :])
+
+        @contextlib.contextmanager
+        def swap():
+            model.lm_head = _LastRow()
+            try:
+                yield
+            finally:
+                model.lm_head = head
+
+        return swap()
 
     # ---------------------------------------------------------------- sampler bound to this model (speculation)
     def _drop_speculation(self, rewind: bool = False):

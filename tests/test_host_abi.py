@@ -224,3 +224,57 @@ def test_fused_decode_wrapper_host_logic():
         else:
             raise AssertionError("FusedDecodeModel accepted a model the fused step cannot take")
         assert isinstance(accelerate(bad), GraphDecodeModel)
+
+
+def test_fused_wrapper_prefill_last_position_only():
+    """FusedDecodeModel(last_logits_only=True): the prefill goes through the UNMODIFIED reference forward with lm_head
+    applied to the last position only.  Runs the real reference model on CPU (its torch path):
+    logits [1, 1, V] bit-equal to the last row of the full forward, the module tree restored afterwards."""
+    import sys
+
+    import torch
+
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    from chatglm_q.int4.qlinear import DynamicQuantizeLinear, QEmbedding
+    from chatglm_q.int4.quantizer import quantize_int4
+    from chatglm_q.loader import create_quant_int4_model
+    from chatglm_q.model import ChatGLM2Config
+
+    from chatglm_q_b200.fused_decode import FusedDecodeModel
+
+    torch.manual_seed(3)
+    cfg = ChatGLM2Config(hidden_size=128, inner_hidden_size=256, head_hidden_size=64, num_multi_query_groups=2,
+                         num_attention_heads=2, num_layers=2, vocab_size=256, max_sequence_length=64)
+    model = create_quant_int4_model(cfg, 32, torch.float32)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, DynamicQuantizeLinear):
+                q, s = quantize_int4(torch.randn(mod.in_features, mod.out_features) / mod.in_features ** 0.5)
+                mod.apply_weights_(q, s, torch.zeros(mod.out_features) if mod.bias is not None else None)
+            elif isinstance(mod, QEmbedding):
+                q, s = quantize_int4(torch.randn(cfg.vocab_size, cfg.hidden_size))
+                mod.apply_weights_(q, s)
+    model.eval()
+    # fp32 CPU model: the fused STEP cannot take it (TypeError), the prefill wrapper logic is dtype-agnostic
+    with pytest.raises(TypeError):
+        FusedDecodeModel(model)
+    for m in model.modules():
+        if isinstance(m, (DynamicQuantizeLinear, QEmbedding)):
+            m.weight_scale.data = m.weight_scale.data.half()
+    model.half()
+    wrapped = FusedDecodeModel(model, max_len=32, last_logits_only=True)
+    head = model.lm_head
+    ids = torch.tensor([[5, 17, 200, 42, 7]])
+    with torch.no_grad():
+        try:
+            _, full, _ = model(input_ids=ids)
+        except RuntimeError as e:           # a CPU build of torch without half matmul: nothing to compare
+            pytest.skip(f"reference CPU forward in fp16 unavailable: {e}")
+        _, last, handle = wrapped(input_ids=ids, past_key_values=None)
+    assert last.shape == (1, 1, cfg.vocab_size) and full.shape == (1, 5, cfg.vocab_size)
+    assert torch.equal(last[0, 0], full[0, -1])
+    assert model.lm_head is head and wrapped.n_valid == 5
