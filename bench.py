@@ -79,15 +79,30 @@ def load_peaks() -> dict:
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def csrc_sha16() -> str:
+    """Hash of the CUDA sources the library is built from: ncu summaries under profiles/ are stamped with it, so a
+    number measured on another build is never reported as this build's."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "chatglm_q_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the decode kernel, from the committed ncu
-    launch list of this same step (profiles/r01_token_summary.json, scripts/gpu_profile.sh); None if absent."""
-    p = ROOT / "profiles" / "r01_token_summary.json"
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the decode kernel, source) from the committed ncu
+    launch list of this same step (profiles/r02_token_summary.json, scripts/gpu_profile2.sh).  Only a summary stamped
+    with THIS build's source hash counts; anything else is reported as null with the reason."""
+    p = ROOT / "profiles" / "r02_token_summary.json"
     try:
         d = json.loads(p.read_text())
-        return round(float(d["dram_bytes"]) / int(d["launches"]))
+        if d.get("csrc_sha16") != csrc_sha16():
+            return None, f"profiles/{p.name} was taken on another build (csrc {d.get('csrc_sha16')} != {csrc_sha16()})"
+        return round(float(d["dram_bytes"]) / int(d["launches"])), f"profiles/{p.name} (ncu launch list, same csrc hash)"
     except (OSError, KeyError, ValueError, ZeroDivisionError):
-        return None
+        return None, "no ncu launch list committed for this build"
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -213,6 +228,37 @@ def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392
     out = []
     gen = torch.Generator(device=device).manual_seed(7)
     stream = torch.cuda.Stream(device=device)
+    # GPU-vs-GPU baseline: the reference's own Triton kernel (chatglm_q/int4/triton_ops.py:90-139, unmodified, from
+    # baseline/_ref) on the same inputs, timed the same way
+    tri, tri_err = None, None
+    try:
+        if import_reference() is None:
+            raise ImportError("baseline/_ref missing")
+        from chatglm_q.int4.triton_ops import dynamic_quant_matmul_s4 as tri
+    except Exception as e:  # noqa: BLE001 -- a Triton that cannot import is a finding to report, not a crash
+        tri_err = f"{type(e).__name__}: {e}"[:300]
+
+    def timed(fn, use):
+        with torch.cuda.stream(stream), torch.no_grad():
+            for i in range(use):
+                fn(i)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(use):
+                    fn(i)
+            for _ in range(3):
+                g.replay()
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters):
+                g.replay()
+            e1.record(stream)
+            stream.synchronize()
+        del g
+        return e0.elapsed_time(e1) * 1e3 / (iters * use)
+
     for n in ns:
         per = k * n // 2 + (k // 32) * n * 2
         copies = max(2, -(-400_000_000 // per))
@@ -220,32 +266,27 @@ def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392
         for m in seqs:
             use = copies if m <= 8 else min(copies, 4)   # M > 8 is tensor-bound: L2 residency is irrelevant
             a = torch.randn((m, k), device=device, generator=gen).half()
-            with torch.cuda.stream(stream), torch.no_grad():
-                for i in range(use):
-                    ops.dynamic_quant_matmul_s4(a, ws[i][0], ws[i][1])
-                stream.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
-                    for i in range(use):
-                        ops.dynamic_quant_matmul_s4(a, ws[i][0], ws[i][1])
-                for _ in range(3):
-                    g.replay()
-                stream.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(iters):
-                    g.replay()
-                e1.record(stream)
-                stream.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / (iters * use)
+            us = timed(lambda i: ops.dynamic_quant_matmul_s4(a, ws[i][0], ws[i][1]), use)
             by, fl = w4_bytes(m, k, n, False), 2.0 * m * n * k
-            out.append({"M": m, "K": k, "N": n, "us": round(us, 2),
-                        "GBps": round(by / us / 1e3, 1), "TFLOPs": round(fl / us / 1e6, 2),
-                        "hbm_frac": round(by / us / 1e3 / peaks["hbm_gbs"], 3),
-                        "tensor_frac": round(fl / us / 1e6 / peaks["bf16_tflops"], 4),
-                        "kernel": "w4_gemv_kernel (mma.sync, TMA ring, cluster DSMEM reduce)" if m <= 8
-                                  else "wq_gemm_tc_kernel (tcgen05 + TMEM)"})
-            del a, g
+            row = {"M": m, "K": k, "N": n, "us": round(us, 2),
+                   "GBps": round(by / us / 1e3, 1), "TFLOPs": round(fl / us / 1e6, 2),
+                   "hbm_frac": round(by / us / 1e3 / peaks["hbm_gbs"], 3),
+                   "tensor_frac": round(fl / us / 1e6 / peaks["bf16_tflops"], 4),
+                   "kernel": "w4_gemv_kernel (mma.sync, TMA ring, cluster DSMEM reduce)" if m <= 8
+                             else "wq_gemm_tc_kernel (tcgen05 + TMEM)"}
+            if tri is not None:
+                try:
+                    tus = timed(lambda i: tri(a, ws[i][0], ws[i][1], allow_tf32=False), use)
+                    row["triton_us"] = round(tus, 2)
+                    row["speedup_vs_reference_triton"] = round(tus / us, 2)
+                except Exception as e:  # noqa: BLE001
+                    tri_err = f"{type(e).__name__}: {e}"[:300]
+                    tri = None
+            if tri is None:
+                row["triton_us"] = None
+                row["triton_error"] = tri_err
+            out.append(row)
+            del a
         del ws
         torch.cuda.empty_cache()
     return out
@@ -318,7 +359,6 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     from chatglm_q_b200.install import install
     import chatglm_q.decoder as decmod
 
-    install("chatglm_q")
     cfg, model = build_ref_int4_model(torch, device)
     real_perf = time.perf_counter
 
@@ -354,6 +394,20 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     from chatglm_q_b200.fused_decode import FusedDecodeModel
 
     tok = StubTokenizer(prompt_len)
+    # GPU-vs-GPU baseline first, before anything of this repo is bound: the UNMODIFIED reference model + decoder on
+    # its own Triton kernels (chatglm_q/int4/triton_ops.py), eager -- what a user of the reference gets on this B200
+    ref_triton = {"value": None}
+    try:
+        import chatglm_q.int4.qlinear as _q4
+
+        assert _q4.KERNEL_IMPL == "triton", f"reference kernel impl is {_q4.KERNEL_IMPL!r}"
+        v, pf, _ = run(ChatGLMDecoder(cfg, model, tok, device=device, time_log=False))
+        ref_triton = {"value": v, "prefill_s": pf, "unit": UNIT,
+                      "how": "unmodified reference model + decoder on the reference's own Triton kernels (no install()), "
+                             "eager, same prompt / tokens / sampler"}
+    except Exception as e:  # noqa: BLE001 -- Triton failing to compile the reference kernels is a finding
+        ref_triton = {"value": None, "error": f"{type(e).__name__}: {e}"[:400]}
+    install("chatglm_q")
     eager, eager_prefill, _ = run(ChatGLMDecoder(cfg, model, tok, device=device, time_log=False))
     graphed, graphed_prefill, _ = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
                                                      tok, device=device, time_log=False))
@@ -417,6 +471,7 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
                                                         "(device=None) hands back; the GPU does not idle across the host "
                                                         "round trip"},
             "fused_step_device_us": dev_us, "fused_step_launches": launches,
+            "reference_triton": ref_triton,
             "graphed_reference_forward": {"value": graphed, "prefill_s": graphed_prefill,
                                           "how": "same decoder, unmodified model forward captured in one CUDA graph "
                                                  "(chatglm_q_b200.GraphDecodeModel), ~1100 kernels per token"},
@@ -426,9 +481,11 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
 
 # ----------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_step(threads: int):
-    """One bounded sample of the step on host cores: ONE transformer block's four linears plus
-    lm_head through the reference's own CPU path (`A.matmul(unpack_int4(B, scale))`,
-    chatglm_q/int4/qlinear.py:47-50), fp16 like the GPU arm.  Token time = 28 x block + lm_head."""
+    """The step on host cores through the reference's own CPU path (`A.matmul(unpack_int4(B, scale))`,
+    chatglm_q/int4/qlinear.py:47-50), fp16 like the GPU arm.  `step(blocks)` runs `blocks` transformer blocks' four
+    linears (the 28 blocks of the model reuse ONE block's weights: 3.4 GB of packed weights x the fp16 unpack
+    temporaries do not need 28 copies to be timed; the 57 MB of a block exceed the host caches) plus lm_head and
+    returns (seconds for the blocks, seconds for lm_head)."""
     import torch
 
     torch.set_num_threads(threads)
@@ -460,43 +517,62 @@ def cpu_reference_step(threads: int):
     lm = make(head[1], head[2], False)
     x = torch.randn(1, H).half()
 
-    def step():
+    def step(blocks: int = LAYERS):
         with torch.no_grad():
             t0 = time.perf_counter()
-            qkv = mods[0](x)
-            o = mods[1](qkv[:, :H].contiguous())
-            hin = mods[2](o)
-            y = mods[3](hin[:, :INNER].contiguous())
+            y = x
+            for _ in range(blocks):
+                qkv = mods[0](y)
+                o = mods[1](qkv[:, :H].contiguous())
+                hin = mods[2](o)
+                y = mods[3](hin[:, :INNER].contiguous())
+                y = y / y.float().abs().max().clamp_min(1e-3).half()      # keep the synthetic chain finite
             t1 = time.perf_counter()
             lm(y)
             t2 = time.perf_counter()
-        return LAYERS * (t1 - t0) + (t2 - t1), t2 - t0
+        return t1 - t0, t2 - t1
 
     return step, kind
 
 
+WORKLOAD = ("ChatGLM2-6B int4g32 bs=1 decode token: 113 QLinear calls at M=1 "
+            "(28 x qkv/o/w_in/w_out + lm_head), random-init packed weights")
+
+
+def bench_config(world: int, graph: bool = True) -> dict:
+    """The workload description BOTH arms print (the driver compares them)."""
+    return {"workload": WORKLOAD,
+            "parallelism": "single GPU" if world == 1 else f"tp{world} (column/row split, 2 reductions per block)",
+            "l2": "inputs larger than L2: 3.36 GB of distinct weights per step vs 126 MB L2"}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on this box's host cores: every step is ONE FULL decode
+    token (28 blocks + lm_head), so `ms_per_step` is the measured wall time of a step and value = 1000 / ms_per_step
+    -- nothing is extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     step, kind = cpu_reference_step(threads)
-    for _ in range(max(1, min(args.warmup, 3))):
-        step()
-    tok_s, wall = [], 0.0
+    for _ in range(max(1, min(args.warmup, 2))):
+        step(2)                                   # warm-up: two blocks + lm_head (allocator, thread pool)
+    walls, blk, head = [], 0.0, 0.0
     for _ in range(args.steps):
-        t, w = step()
-        tok_s.append(t)
-        wall += w
-    per_tok = sum(tok_s) / len(tok_s)
+        tb, th = step(LAYERS)
+        walls.append(tb + th)
+        blk += tb
+        head += th
+    per_tok = sum(walls) / len(walls)
     value = 1.0 / per_tok
-    sample = (f"per step: 1 of 28 blocks (qkv,o,w_in,w_out) + lm_head at M=1 fp16 through the reference CPU path; "
-              f"token time = 28 x block + lm_head; {args.steps} steps, {wall:.1f} s of CPU work")
+    sample = (f"every step = one full token: 28 x (qkv,o,w_in,w_out) + lm_head at M=1 fp16 through the reference CPU path "
+              f"(chatglm_q/int4/qlinear.py:47-50); {args.steps} steps, {sum(walls):.1f} s of CPU work "
+              f"(blocks {blk:.1f} s, lm_head {head:.1f} s)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(per_tok * 1e3, 2),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic", "config": {"workload": "ChatGLM2-6B int4g32 bs=1 decode token: 113 QLinear calls at M=1"},
+        "data": "synthetic", "config": bench_config(args.gpus),
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -574,7 +650,8 @@ def run_own_arm(args):
     roofline = {"bound": "hbm", "kernel": "w4_gemv_kernel", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                 "frac_of_8TBps_nominal": round(achieved / 8000.0, 4), "peak_source": peaks["source"],
-                "traffic": ncu_traffic_per_launch() if world == 1 else None,
+                "traffic": ncu_traffic_per_launch()[0] if world == 1 else None,
+                "traffic_source": ncu_traffic_per_launch()[1] if world == 1 else "N>1: not captured",
                 "algorithmic_bytes_per_launch": round(total_bytes / step.launches),
                 "algorithmic_bytes_per_step": total_bytes, "launches_per_step": step.launches,
                 "avg_launch_us": round(ms_per_step * 1e3 / step.launches, 3),
@@ -588,11 +665,8 @@ def run_own_arm(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "ChatGLM2-6B int4g32 bs=1 decode token: 113 QLinear calls at M=1 "
-                                   "(28 x qkv/o/w_in/w_out + lm_head), random-init packed weights",
-                       "parallelism": "single GPU" if world == 1 else f"tp{world} (column/row split, 2 all-reduce per block)",
-                       "l2": "inputs larger than L2: 3.36 GB of distinct weights per step vs 126 MB L2",
-                       "launch": "no CUDA graph" if args.no_graph else "CUDA graph replay of the 113 C-ABI launches"},
+            "config": bench_config(world),
+            "launch": "no CUDA graph" if args.no_graph else "CUDA graph replay of the C-ABI launches",
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(roofline["launches_per_step"] * args.steps),
         }
     if world == 1:
@@ -603,16 +677,20 @@ def run_own_arm(args):
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             cstep, kind = cpu_reference_step(threads)
-            cstep()
-            ts, wall = [], 0.0
-            while wall < 12.0 and len(ts) < 20:
-                t, w = cstep()
-                ts.append(t)
-                wall += w
-            per = sum(ts) / len(ts)
+            cstep(1)
+            nb, tb, th, reps = 4, 0.0, 0.0, 0
+            while tb + th < 12.0 and reps < 20:      # bounded sample: 4 of the 28 blocks + lm_head per repetition
+                b, h_ = cstep(nb)
+                tb += b
+                th += h_
+                reps += 1
+            per = LAYERS * (tb / (reps * nb)) + th / reps
             line["cpu_baseline"] = {"value": round(1.0 / per, 4), "unit": UNIT, "cores": threads, "kind": kind,
-                                    "sample": f"{len(ts)} x (1 of 28 blocks + lm_head) at M=1 fp16 through the reference "
-                                              f"CPU path, token time = 28 x block + lm_head; {wall:.1f} s of CPU work"}
+                                    "measured_block_ms": round(tb / (reps * nb) * 1e3, 2),
+                                    "measured_lm_head_ms": round(th / reps * 1e3, 2), "layers": LAYERS,
+                                    "sample": f"{reps} x ({nb} of 28 blocks + lm_head) at M=1 fp16 through the reference "
+                                              f"CPU path; token time DERIVED = 28 x measured block + lm_head; "
+                                              f"{tb + th:.1f} s of CPU work (`--impl reference` times full tokens)"}
     else:
         # e2e at N>1: the same TP step fed from pinned host memory and read back every step.  A watchdog makes
         # sure a stuck collective can never hang the bench: the line is then printed without the e2e number.

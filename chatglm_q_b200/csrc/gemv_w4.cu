@@ -813,9 +813,11 @@ int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
     if (trick) return launch_m1<T, kIsHalf>(a, tmW, tmS, prm, grid, stages, pdl, pro);
     return launch_m1<T, false>(a, tmW, tmS, prm, grid, stages, pdl, pro);
   }
-  // M > 1 always takes the exact (q - 8) dequant.  The subnormal-operand variant of this path gave
-  // run-to-run different results for M >= 5 whenever several CTAs shared an SM (stress test
-  // tests/test_gpu_parity.py::test_decode_kernel_stress; the exact variant never did), so it is not built.
+  // M > 1 takes the exact (q - 8) dequant by default.  The subnormal-operand variant of this path was seen to give
+  // run-to-run different results for M >= 5 -- on the build that still had the ring-release race;
+  // CGQ_GEMV_TRICK_MGT1=1 selects it for the root-cause experiment (scripts/gpu_sanitize.sh).
+  static const bool trick_mgt1 = env_int("CGQ_GEMV_TRICK_MGT1", 0, 0, 1) != 0;
+  if (trick && trick_mgt1) return launch_inst<T, kIsHalf, false, PRO_NONE>(a, tmW, tmS, prm, grid, stages, pdl);
   return launch_inst<T, false, false, PRO_NONE>(a, tmW, tmS, prm, grid, stages, pdl);
 }
 
