@@ -30,6 +30,10 @@ SYMBOLS = {
     "cgq_program_run": (c_int, [ctypes.c_uint64, c_void_p]),
     "cgq_program_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p]),
     "cgq_program_destroy": (c_int, [ctypes.c_uint64]),
+    "cgq_step_create": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "cgq_step_run": (c_int, [ctypes.c_uint64, c_void_p]),
+    "cgq_step_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p, c_void_p]),
+    "cgq_step_destroy": (c_int, [ctypes.c_uint64]),
     "cgq_prefetch_next_w4": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "cgq_decode_begin_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p]),
@@ -56,6 +60,18 @@ class LinearOp(ctypes.Structure):
     _fields_ = [("Wq", c_void_p), ("scale", c_void_p), ("bias", c_void_p), ("A", c_void_p), ("C", c_void_p),
                 ("resid", c_void_p), ("norm_w", c_void_p), ("N", c_int), ("K", c_int), ("prologue", c_int),
                 ("eps", c_float)]
+
+
+STEP_LINEAR, STEP_ATTENTION, STEP_EMBED = 0, 1, 2
+
+
+class StepOp(ctypes.Structure):
+    """`cgq_step_op` of include/cgq.h (one phase of the one-launch decode step)."""
+    _fields_ = [("kind", c_int), ("Wq", c_void_p), ("scale", c_void_p), ("bias", c_void_p), ("A", c_void_p),
+                ("C", c_void_p), ("resid", c_void_p), ("norm_w", c_void_p), ("N", c_int), ("K", c_int),
+                ("prologue", c_int), ("eps", c_float), ("freqs", c_void_p), ("kcache", c_void_p), ("vcache", c_void_p),
+                ("n_head", c_int), ("n_groups", c_int), ("d_head", c_int), ("max_len", c_int), ("ids", c_void_p),
+                ("V", c_int)]
 
 
 class CgqError(RuntimeError):

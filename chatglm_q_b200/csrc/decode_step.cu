@@ -29,7 +29,7 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(256)
     decode_begin_w4_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ Wq,
-                           const T* __restrict__ scale, T* __restrict__ x, int D, int group,
+                           const T* __restrict__ scale, T* __restrict__ x, int V, int D, int group,
                            int* __restrict__ state) {
   // First kernel of the step's graph: everything before it has completed.  The position is published
   // (written + fenced) BEFORE the dependents are released, so that the attention kernels further down the
@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   ptx::pdl_launch_dependents();
-  const int64_t t = ids[0];
+  int64_t t = ids[0];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);   // an id outside the vocabulary must never read out of bounds
   const uint8_t* wrow = Wq + (t >> 1) * D;
   const T* srow = scale + (t / group) * D;
   const int shift = static_cast<int>(t & 1) * 4;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   const int g = h / hpg;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   attn_stamp(p, 0);
+  if (p.splits > 1) ptx::cluster_arrive_release();   // phase A: waited for before the first DSMEM store (racecheck)
   ptx::pdl_launch_dependents();
   // Everything that does not depend on this step's qkv is requested BEFORE the dependency wait, while the
   // qkv projection is still running: the position (published by decode_begin ahead of its own dependents),
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
     }
   }
   if (S > 1) {
+    ptx::cluster_wait_acquire();                    // every CTA of the cluster is running (phase A)
     if (t < DH) ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xacc + rank * DH + t), 0), o);
     if (t == 0) {
       ptx::st_cluster_f32(ptx::mapa_rank(ptx::smem_u32(xstat + rank), 0), M);
@@ -398,10 +401,10 @@ extern "C" int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq, const 
   const dim3 grid((D + 255) / 256), block(256);
   if (dtype == CGQ_DTYPE_F16)
     return launch_pdl(decode_begin_w4_kernel<__half>, grid, block, 0, st, ids, Wq,
-                      static_cast<const __half*>(scale), static_cast<__half*>(x), D, group, state);
+                      static_cast<const __half*>(scale), static_cast<__half*>(x), V, D, group, state);
   if (dtype == CGQ_DTYPE_BF16)
     return launch_pdl(decode_begin_w4_kernel<__nv_bfloat16>, grid, block, 0, st, ids, Wq,
-                      static_cast<const __nv_bfloat16*>(scale), static_cast<__nv_bfloat16*>(x), D,
+                      static_cast<const __nv_bfloat16*>(scale), static_cast<__nv_bfloat16*>(x), V, D,
                       group, state);
   set_error("cgq_decode_begin_w4: bad dtype %d", dtype);
   return CGQ_ERR_BAD_DTYPE;

@@ -44,7 +44,7 @@ struct SampleParams {
   int vpad;             // V rounded up to a multiple of 64 * kWarps
   int k;                // min(top_k, V)
   float top_p;
-  float inv_temp;
+  float temperature;   // logits are DIVIDED by it, like the reference (decoder.py:14), not multiplied by 1/T
   const float* q;       // [k] Exp(1) variates or null
   long long* token;     // [1] or null
   float* probs;         // [k] or null
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
   const uint32_t tau = (ta << 8) | sel[10];
   uint32_t gmax = redu[lane];
   gmax = __reduce_max_sync(kFull, gmax);
-  const float vmax = key_to_float<T>(gmax) * p.inv_temp;
+  const float vmax = key_to_float<T>(gmax) / p.temperature;
 
   // ---- F2: sum of exponentials, candidates = every element >= tau
   float se = 0.f;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
     for (int h = 0; h < 2; ++h) {
       const uint32_t key = (kk >> (16 * h)) & 0xffffu;
       const bool valid = e0 + h < V;
-      if (valid) se += expf(key_to_float<T>(key) * p.inv_temp - vmax);
+      if (valid) se += expf(key_to_float<T>(key) / p.temperature - vmax);
       const bool cand = valid && key >= tau;
       const uint32_t bc = __ballot_sync(kFull, cand);
       if (bc != 0) {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) top_p_sample_kernel(const SampleP
     for (int j = 0; j < n_cand; ++j) r += comp[j] > mine ? 1 : 0;
     if (r < k) {
       const uint32_t key = static_cast<uint32_t>(mine >> 32);
-      sp[r] = expf(key_to_float<T>(key) * p.inv_temp - vmax) / sumexp;
+      sp[r] = expf(key_to_float<T>(key) / p.temperature - vmax) / sumexp;
       sidx[r] = static_cast<int>(0xffffffffu - static_cast<uint32_t>(mine));
     }
   }
@@ -420,7 +420,7 @@ extern "C" int cgq_top_p_sample(const void* logits, int V, int dtype, int top_k,
     set_error("cgq_top_p_sample: a token is requested without the Exp(1) variates q");
     return CGQ_ERR_BAD_SHAPE;
   }
-  SampleParams p{logits, V, vpad, k, top_p, 1.0f / temperature, q,
+  SampleParams p{logits, V, vpad, k, top_p, temperature, q,
                  reinterpret_cast<long long*>(token), probs, reinterpret_cast<long long*>(indices)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CGQ_DTYPE_F16) return launch_sample<__half>(p, st);

@@ -39,10 +39,13 @@ _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 
 
 class _FusedCache:
-    """Opaque `past_key_values` handle returned to the decoder (the state lives in the wrapper)."""
+    """Opaque `past_key_values` handle returned to the decoder (the state lives in the wrapper).  Stamped with the
+    wrapper's epoch: a handle from an earlier `generate()` (another prefill has replaced the cache since) is treated
+    like no cache at all instead of silently continuing on the newer session's rows."""
 
     def __init__(self, owner: "FusedDecodeModel"):
         self.owner = owner
+        self.epoch = owner._epoch
 
 
 def _is_w4_linear(m) -> bool:
@@ -53,8 +56,20 @@ def _is_w4_linear(m) -> bool:
 
 class FusedDecodeModel:
     def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None,
-                 speculate: bool = False, last_logits_only: bool = False):
+                 speculate: bool = False, last_logits_only: bool = False, alias_logits: bool | None = None):
         cfg = model.config
+        # The fused step writes its logits into ONE static buffer.  The reference returns a fresh tensor per call, so
+        # by default the wrapper hands out a copy (130 KB); `alias_logits=True` returns the static buffer itself (it is
+        # overwritten by the next step -- fine for ChatGLMDecoder.generate, which samples at once).  The speculative
+        # sampler recognises "the logits of the step in flight" by that buffer, so speculate=True implies aliasing.
+        self.alias_logits = bool(speculate) if alias_logits is None else bool(alias_logits)
+        if speculate and not self.alias_logits:
+            raise ValueError("FusedDecodeModel(speculate=True) needs alias_logits=True")
+        self._epoch = 0
+        # One launch per token (cgq_step_*, csrc/decode_mk.cu) when the model fits it (fp16, every N a multiple of 32,
+        # K <= 13824); otherwise -- or with CGQ_ONE_LAUNCH=0 -- the PDL-chained 5 x layers + 2 launches.
+        self.one_launch = bool(int(os.environ.get("CGQ_ONE_LAUNCH", "1") or 1))
+        self._step_handle = None
         # last_logits_only=True: a prefill (several tokens) computes lm_head for the LAST position only and returns
         # logits [1, 1, V] -- all ChatGLMDecoder.generate reads is logits[0, -1] (decoder.py:85); at 2 048 tokens that
         # is 1.09 TFLOP and a 266 MB logits tensor less.  Off by default: the reference returns
@@ -132,6 +147,9 @@ class FusedDecodeModel:
         assert self.freqs.dtype == dt and self.freqs.is_contiguous() and self.freqs.shape[1] == DH
         self.device = device
         self.graph = None
+        self._drop_step()                 # the step program holds the old buffers' addresses
+        if dt != torch.float16:
+            self.one_launch = False
         self._ready = True
 
     # ---------------------------------------------------------------- the step, as C-ABI calls
@@ -155,10 +173,69 @@ class FusedDecodeModel:
             None if norm is None else norm.weight.data_ptr(), float(norm.eps) if norm is not None else 0.0,
             stream))
 
+    def _build_step(self):
+        """The whole token step as a `cgq_step_op` array (include/cgq.h) -> one persistent cooperative kernel."""
+        import ctypes
+
+        from ._lib import STEP_ATTENTION, STEP_EMBED, STEP_LINEAR, StepOp
+
+        lib = _lib.load()
+        cfg, m = self.cfg, self.model
+        ops = []
+
+        def lin(l, a, out, pro=PRO_NONE, norm=None, resid=None):
+            k2, n = l.weight.shape
+            bias = getattr(l, "bias", None)
+            ops.append(StepOp(kind=STEP_LINEAR, Wq=l.weight.data_ptr(), scale=l.weight_scale.data_ptr(),
+                              bias=None if bias is None else bias.data_ptr(), A=a.data_ptr(), C=out.data_ptr(),
+                              resid=None if resid is None else resid.data_ptr(),
+                              norm_w=None if norm is None else norm.weight.data_ptr(), N=n, K=2 * k2, prologue=pro,
+                              eps=float(norm.eps) if norm is not None else 0.0))
+
+        emb = m.word_embedding
+        ops.append(StepOp(kind=STEP_EMBED, Wq=emb.weight.data_ptr(), scale=emb.weight_scale.data_ptr(),
+                          C=self.x.data_ptr(), N=emb.weight.shape[1], V=emb.weight.shape[0] * 2, ids=self.ids.data_ptr()))
+        for layer, (kc, vc) in zip(m.layers, self.kv):
+            lin(layer.attn.qkv_proj, self.x, self.qkv, PRO_RMSNORM, layer.attn_ln)
+            ops.append(StepOp(kind=STEP_ATTENTION, A=self.qkv.data_ptr(), C=self.ao.data_ptr(), freqs=self.freqs.data_ptr(),
+                              kcache=kc.data_ptr(), vcache=vc.data_ptr(), n_head=cfg.num_attention_heads,
+                              n_groups=cfg.num_multi_query_groups, d_head=cfg.head_hidden_size, max_len=self.max_len))
+            lin(layer.attn.o_proj, self.ao, self.x, resid=self.x)
+            lin(layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln)
+            lin(layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x)
+        lin(m.lm_head, self.x, self.logits, PRO_RMSNORM, m.final_ln)
+        arr = (StepOp * len(ops))(*ops)
+        handle = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            rc = lib.cgq_step_create(arr, len(ops), self.code, self.state.data_ptr(), ctypes.byref(handle))
+        if rc != 0:
+            return None, (lib.cgq_last_error() or b"").decode()
+        return handle.value, ""
+
+    def _drop_step(self):
+        handle = self.__dict__.get("_step_handle")       # (never through __getattr__: it forwards to the model)
+        if handle is not None:
+            try:
+                _lib.load().cgq_step_destroy(handle)
+            except Exception:  # noqa: BLE001 -- interpreter shutdown
+                pass
+            self.__dict__["_step_handle"] = None
+
+    def __del__(self):
+        self._drop_step()
+
     def _launch_step(self):
         lib = _lib.load()
         cfg, m = self.cfg, self.model
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.one_launch and self._step_handle is None:
+            self._step_handle, why = self._build_step()
+            if self._step_handle is None:       # a shape the step program does not take: the launch-per-op chain
+                self.one_launch = False
+                self.one_launch_refused = why
+        if self.one_launch:
+            _lib.check(lib.cgq_step_run(self._step_handle, stream))
+            return
         emb = m.word_embedding
         _lib.check(lib.cgq_decode_begin_w4(
             self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
@@ -189,7 +266,7 @@ class FusedDecodeModel:
                    wait=prev_out if self.hand_mask & 4 else None)
 
     def launches_per_step(self) -> int:
-        return 5 * self.cfg.num_layers + 2
+        return 1 if (self.one_launch and self._step_handle is not None) else 5 * self.cfg.num_layers + 2
 
     def _capture(self):
         dev = self.device
@@ -213,9 +290,13 @@ class FusedDecodeModel:
             return self.model(input_ids=input_ids, past_key_values=past_key_values, **kwargs)
         on_host = input_ids.device.type == "cpu"
         dev = self.model.lm_head.weight.device
-        fresh = past_key_values is None or not isinstance(past_key_values, _FusedCache)
+        fresh = (past_key_values is None or not isinstance(past_key_values, _FusedCache)
+                 or past_key_values.owner is not self or past_key_values.epoch != self._epoch)
         if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
+            # prefill, several new tokens or a batch: the unmodified model, on the cache wherever it lives
             self._drop_speculation()
+            if fresh:
+                self._epoch += 1
             with self._last_position_head():
                 loss, logits, kv = self.model(input_ids=input_ids.to(dev),
                                               past_key_values=None if fresh else self._export_kv())
@@ -227,12 +308,14 @@ class FusedDecodeModel:
             if on_host and int(input_ids[0, 0]) == self._spec_token:
                 self.n_valid += 1
                 self._host_ids = True
-                return None, self.logits, past_key_values
+                return None, self._out_logits(), past_key_values
             self._drop_speculation(rewind=True)      # another token: take the step back, run the right one
         if self._eager_kv is not None or self.n_valid + 1 > self.max_len:
+            # static window exhausted (or a cache the static buffers cannot hold): the unmodified model from here on
             if self._eager_kv is None:
                 self._eager_kv = self._export_kv()
             loss, logits, self._eager_kv = self.model(input_ids=input_ids.to(dev), past_key_values=self._eager_kv)
+            self.n_valid = self._eager_kv[0][0].shape[1]
             return loss, logits, past_key_values
         self._host_ids = on_host
         self.ids.copy_(input_ids, non_blocking=True)
@@ -240,7 +323,10 @@ class FusedDecodeModel:
             self._capture()
         self.graph.replay()
         self.n_valid += 1
-        return None, self.logits, past_key_values
+        return None, self._out_logits(), past_key_values
+
+    def _out_logits(self):
+        return self.logits if self.alias_logits else self.logits.clone()
 
     def _last_position_head(self):
         """Context manager: while active, `model.lm_head` only sees the last position of its input (the unmodified
@@ -336,6 +422,8 @@ class FusedDecodeModel:
         self.state.copy_(torch.tensor([n, n], dtype=torch.int32), non_blocking=False)
 
     def _export_kv(self):
+        if self._eager_kv is not None:      # the cache lives outside the static buffers (batch > 1, window exhausted)
+            return self._eager_kv
         n = self.n_valid
         return tuple((k[:, :n].clone(), v[:, :n].clone()) for k, v in self.kv)
 

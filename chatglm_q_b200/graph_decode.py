@@ -29,6 +29,7 @@ class _GraphCache:
 
     def __init__(self, owner: "GraphDecodeModel"):
         self.owner = owner
+        self.epoch = owner._epoch
 
 
 class GraphDecodeModel:
@@ -37,7 +38,8 @@ class GraphDecodeModel:
         self.max_len = int(max_len)
         self.graph: torch.cuda.CUDAGraph | None = None
         self.n_valid = 0
-        self._eager_kv = None      # set when the window is exhausted: plain reference path from then on
+        self._eager_kv = None      # set when the window is exhausted / the batch is > 1: plain reference path
+        self._epoch = 0
 
     # nn.Module-ish surface the decoder / loader touch
     def __getattr__(self, name):
@@ -83,9 +85,12 @@ class GraphDecodeModel:
     def __call__(self, input_ids: Tensor = None, past_key_values=None, **kwargs):
         if kwargs or input_ids is None:
             return self.model(input_ids=input_ids, past_key_values=past_key_values, **kwargs)
-        fresh = past_key_values is None or not isinstance(past_key_values, _GraphCache)
+        fresh = (past_key_values is None or not isinstance(past_key_values, _GraphCache)
+                 or past_key_values.owner is not self or past_key_values.epoch != self._epoch)
         if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
             # prefill through the unmodified model, then move its cache into the static window
+            if fresh:
+                self._epoch += 1
             loss, logits, kv = self.model(input_ids=input_ids,
                                           past_key_values=None if fresh else self._export_kv())
             self._import_kv(kv, input_ids.device, logits)
@@ -95,20 +100,21 @@ class GraphDecodeModel:
             if self._eager_kv is None:
                 self._eager_kv = self._export_kv()
             loss, logits, self._eager_kv = self.model(input_ids=input_ids, past_key_values=self._eager_kv)
+            self.n_valid = self._eager_kv[0][0].shape[1]
             return loss, logits, past_key_values
         self.ids.copy_(input_ids, non_blocking=True)
         if self.graph is None:
             self._capture()
         self.graph.replay()
         self.n_valid += 1
-        return None, self.logits, past_key_values
+        return None, self.logits.clone(), past_key_values      # a fresh tensor per step, like the reference
 
     # ---------------------------------------------------------------- cache import / export
     def _import_kv(self, kv, device, logits):
         n = kv[0][0].shape[1]
         L = self.max_len - 1
         self._eager_kv = None
-        if n > L:
+        if n > L or kv[0][0].shape[0] != 1:      # longer than the window, or a batch: the static buffers hold one row
             self._eager_kv = kv
             self.n_valid = n
             return
@@ -131,5 +137,7 @@ class GraphDecodeModel:
         self.n_valid = n
 
     def _export_kv(self):
+        if self._eager_kv is not None:
+            return self._eager_kv
         n, L = self.n_valid, self.max_len - 1
         return tuple((k[:, L - n:].clone(), v[:, L - n:].clone()) for k, v in self.kv)

@@ -17,6 +17,11 @@ from ._lib import IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_GEMV_UMMA, IMPL_SI
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 _workspaces: dict[tuple[int, int], Tensor] = {}
 _ws_bytes = None
+# Set by install(): the REFERENCE's own implementations (its Triton kernels / its torch sampler), saved before the
+# rebind.  Configurations this library does not build -- fp32 activations, group sizes other than 32, CPU / fp32
+# logits or top_k > 1024 in the sampler -- are handed to them unchanged, so that install() never turns a call that
+# works in the reference into an error.  Not a fallback of this library's own: without install() those inputs raise.
+_delegates: dict[str, object] = {"s4": None, "s8": None, "sampler": None}
 
 
 def check_input(a: Tensor) -> bool:
@@ -77,6 +82,10 @@ def dynamic_quant_matmul_s4(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: b
     M, K = a.shape
     G, N = b_scale.shape
     group = K // G
+    if (group != 32 or a.dtype not in _DTYPE_CODE) and _delegates["s4"] is not None and bias is None:
+        # fp32 / TF32 activations and other power-of-two groups exist in the reference (int4/triton_ops.py:120-123,
+        # loader.create_quant_int4_model(group_size=...)): its own kernel keeps serving them after install()
+        return _delegates["s4"](a.reshape(*output_shape[:-1], K), b, b_scale, allow_tf32)
     assert group == 32, f"only the reference model's group size 32 is built, got {group}"
     code = _dtype_code(a)
     if a.stride(1) != 1 or (M > 1 and a.stride(0) < K):
@@ -126,6 +135,8 @@ def dynamic_quant_matmul(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool
     assert b_scale.get_device() == a.get_device(), f"{b_scale.device=}, {a.device=}"
     M, K = a.shape
     _, N = b.shape
+    if a.dtype not in _DTYPE_CODE and _delegates["s8"] is not None and bias is None:
+        return _delegates["s8"](a.reshape(*output_shape[:-1], K), b, b_scale, allow_tf32)   # fp32: the reference's kernel
     code = _dtype_code(a)
     if a.stride(1) != 1 or (M > 1 and a.stride(0) < K):
         a = a.contiguous()
@@ -295,8 +306,14 @@ def top_p_sampling(logits: Tensor, top_k=100, top_p=0.8, temperature=1.0, *, q: 
     """Drop-in for chatglm_q.decoder.top_p_sampling (chatglm_q/decoder.py:12-27): logits (..., V) fp16 / bf16 on
     the GPU -> sampled token ids (...) int64.  Two launches per call (the Exp(1) draw torch.multinomial would make,
     then cgq_top_p_sample per row) instead of ~15 and a host synchronisation; with the same torch seed it
-    returns the token the reference returns.  `q` (keyword-only, not in the reference): the Exp(1) variates
+    returns the token the reference returns except at fp32 rounding ties (the softmax / cumulative sums are added in
+    another order: a probability sitting exactly on the top-p edge, or two candidates whose p/q agree to the last
+    bit, may resolve differently).  `q` (keyword-only, not in the reference): the Exp(1) variates
     (..., min(top_k, V)) fp32 to use instead of drawing them -- reproducible sampling for tests."""
+    ref = _delegates["sampler"]
+    if ref is not None and q is None and (logits.get_device() < 0 or logits.dtype not in _DTYPE_CODE
+                                          or min(int(top_k), logits.shape[-1]) > 1024 or logits.shape[-1] > 90000):
+        return ref(logits, top_k, top_p, temperature)      # what the one-launch kernel does not take: the reference's own
     return _sample_rows(logits, top_k, top_p, temperature, True, q)
 
 

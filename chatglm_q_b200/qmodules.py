@@ -59,6 +59,7 @@ class W4Linear(_QLinear):
                  device=None, dtype=None):
         super().__init__()
         assert in_features % group_size == 0, f"{in_features=}, {group_size=}"
+        assert group_size == GROUP, f"W4Linear is built for the reference model's group size {GROUP}, got {group_size}"
         self.in_features, self.out_features = in_features, out_features
         self.group_size, self.groups = group_size, in_features // group_size
         self.register_buffer(

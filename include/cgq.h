@@ -208,6 +208,48 @@ int cgq_program_status(uint64_t handle, int* workers, int* failed);
 int cgq_program_destroy(uint64_t handle);
 
 /*
+ * ---- One-launch decode step ("step program"): embedding row + attention + linears of a whole token -----------
+ * The batch-1 token step of the int4g32 model (ChatGLM2Model.forward with past_key_values, model.py:329-392) as ONE
+ * persistent cooperative kernel: one CTA per SM, the TMA producer of every CTA streams the weights of the whole
+ * step through a deep shared-memory ring (HBM keeps streaming across phase boundaries), a linear is cut into
+ * column slices that belong to one CTA each (no cross-CTA reduction), phases are separated by a flat grid barrier
+ * (DESIGN.md §3.10).  Ops run strictly in order; op i may read what ops < i wrote.
+ *   CGQ_STEP_LINEAR     out[N] = (resid +) round(prologue(A) . dequant(Wq, scale)) (+ bias)   -- as cgq_linear_op
+ *   CGQ_STEP_ATTENTION  RoPE, KV append, attention of one query row: A = qkv, C = out           -- as cgq_decode_attention
+ *   CGQ_STEP_EMBED      C[N] = int4 QEmbedding row ids[0] of (Wq [V/2, N], scale [V/32, N])      -- as cgq_decode_begin_w4
+ * `state` ([1] int32, device; may be NULL without attention ops) = tokens in the KV cache before the step; the
+ * kernel reads it at entry and increments it.  fp16 only; N a multiple of 32, K <= 13824.
+ *   cgq_step_create / cgq_step_run (memset + one cooperative launch, graph-capturable) / cgq_step_status
+ *   (synchronises; CTAs, ring stages, whether a barrier ever timed out) / cgq_step_destroy.
+ */
+#define CGQ_STEP_LINEAR 0
+#define CGQ_STEP_ATTENTION 1
+#define CGQ_STEP_EMBED 2
+typedef struct {
+  int kind;             /* CGQ_STEP_* */
+  const uint8_t* Wq;    /* LINEAR: [K/2, N]; EMBED: [V/2, N] */
+  const void* scale;    /* LINEAR: [K/32, N]; EMBED: [V/32, N] */
+  const void* bias;     /* LINEAR: [N] or NULL */
+  const void* A;        /* LINEAR: activation row [K] ([2K] for CGQ_PRO_SILU_GATE); ATTENTION: qkv */
+  void* C;              /* output row */
+  const void* resid;    /* LINEAR: [N] or NULL (may alias C) */
+  const void* norm_w;   /* LINEAR: [K], CGQ_PRO_RMSNORM only */
+  int N, K;             /* EMBED: N = embedding dim */
+  int prologue;         /* CGQ_PRO_* */
+  float eps;
+  const void* freqs;    /* ATTENTION: rotary table [max_pos, d_head] */
+  void* kcache;         /* ATTENTION: [max_len, n_groups, d_head] */
+  void* vcache;
+  int n_head, n_groups, d_head, max_len;
+  const int64_t* ids;   /* EMBED: [1] token id (device) */
+  int V;                /* EMBED: vocabulary size */
+} cgq_step_op;
+int cgq_step_create(const cgq_step_op* ops, int n_ops, int dtype, int* state, uint64_t* handle);
+int cgq_step_run(uint64_t handle, void* stream);
+int cgq_step_status(uint64_t handle, int* ctas, int* stages, int* failed);
+int cgq_step_destroy(uint64_t handle);
+
+/*
  * First launch of a decode step: x[D] = int4 QEmbedding row of token ids[0]
  * (int4/qlinear.py:122-130) and the device-side position bookkeeping:
  *   state[1] = state[0]  (tokens in the KV cache before this step, used by cgq_decode_attention)

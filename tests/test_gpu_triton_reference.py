@@ -141,3 +141,29 @@ def test_reference_triton_matches_its_torch_fallback_fp16(ref):
     tri = t4.dynamic_quant_matmul_s4(at, bt, st, allow_tf32=False)
     want = at.float() @ unpack_int4(bt, st).float()
     assert_parity(from_torch(tri), from_torch(want), "reference Triton vs reference torch path (fp16 inputs)", RTOL)
+
+
+def test_install_keeps_reference_only_configurations_working(ref):
+    """after install() the reference's fp32 (TF32-capable) activations and non-32 group sizes -- which this
+    library does not build -- still run, on the reference's own saved kernels (ops._delegates)."""
+    torch = _torch()
+    from chatglm_q.int4 import qlinear as q4
+    from chatglm_q.int4.quantizer import quantize_int4
+    from chatglm_q_b200.install import install, uninstall
+
+    torch.manual_seed(1)
+    a = torch.randn((4, 512))
+    b = torch.randn((512, 256)) / 512 ** 0.5
+    install("chatglm_q")
+    try:
+        assert q4.KERNEL_IMPL == "cgq_b200"
+        for group in (32, 64):
+            bq, bs = quantize_int4(b, group)
+            want = a @ q4.unpack_int4(bq, bs)
+            got32 = q4.dynamic_quant_matmul(a.cuda(), bq.cuda(), bs.cuda())          # fp32 -> reference Triton
+            assert torch.allclose(got32.cpu(), want, atol=2e-2, rtol=2e-2), f"fp32 group {group}"   # (TF32 allowed by default)
+            got16 = q4.dynamic_quant_matmul(a.half().cuda(), bq.cuda(), bs.half().cuda())   # group 64 -> delegate
+            assert_parity(from_torch(got16), want.numpy(), f"fp16 group {group} after install()", 2e-2)
+    finally:
+        uninstall("chatglm_q")
+    assert q4.KERNEL_IMPL == "triton"

@@ -278,3 +278,91 @@ def test_fused_wrapper_prefill_last_position_only():
     assert last.shape == (1, 1, cfg.vocab_size) and full.shape == (1, 5, cfg.vocab_size)
     assert torch.equal(last[0, 0], full[0, -1])
     assert model.lm_head is head and wrapped.n_valid == 5
+
+
+def _tiny_ref_int4_model(torch):
+    """Random tiny int4g32 ChatGLM2 built by the reference's own factory, fp16 on CPU (its torch path)."""
+    import sys
+
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    from chatglm_q.int4.qlinear import DynamicQuantizeLinear, QEmbedding
+    from chatglm_q.int4.quantizer import quantize_int4
+    from chatglm_q.loader import create_quant_int4_model
+    from chatglm_q.model import ChatGLM2Config
+
+    torch.manual_seed(5)
+    cfg = ChatGLM2Config(hidden_size=128, inner_hidden_size=256, head_hidden_size=64, num_multi_query_groups=2,
+                         num_attention_heads=2, num_layers=2, vocab_size=256, max_sequence_length=64)
+    model = create_quant_int4_model(cfg, 32, torch.float32)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, DynamicQuantizeLinear):
+                q, s = quantize_int4(torch.randn(mod.in_features, mod.out_features) / mod.in_features ** 0.5)
+                mod.apply_weights_(q, s, torch.zeros(mod.out_features) if mod.bias is not None else None)
+            elif isinstance(mod, QEmbedding):
+                q, s = quantize_int4(torch.randn(cfg.vocab_size, cfg.hidden_size))
+                mod.apply_weights_(q, s)
+    for m in model.modules():
+        if isinstance(m, (DynamicQuantizeLinear, QEmbedding)):
+            m.weight_scale.data = m.weight_scale.data.half()
+    model.half().eval()
+    try:
+        with torch.no_grad():
+            model(input_ids=torch.tensor([[1, 2]]))
+    except RuntimeError as e:
+        pytest.skip(f"reference CPU forward in fp16 unavailable: {e}")
+    return cfg, model
+
+
+@pytest.mark.parametrize("wrapper", ["fused", "graph"])
+def test_wrappers_batch_and_long_prompt_stay_on_the_reference_path(wrapper):
+    """calls the static one-row window cannot take -- a batch of 2, a prompt longer than the window, a
+    multi-token call after either -- must run the unmodified model on the cache it returned ("correct, just not
+    fused"), keep `n_valid` in step, and never touch a stale static cache.  Real reference model on CPU."""
+    import torch
+
+    from chatglm_q_b200.fused_decode import FusedDecodeModel
+    from chatglm_q_b200.graph_decode import GraphDecodeModel
+
+    cfg, model = _tiny_ref_int4_model(torch)
+    make = (lambda: FusedDecodeModel(model, max_len=8)) if wrapper == "fused" else (lambda: GraphDecodeModel(model, max_len=8))
+
+    def reference(calls):
+        kv, outs = None, []
+        with torch.no_grad():
+            for ids in calls:
+                _, lg, kv = model(input_ids=ids, past_key_values=kv)
+                outs.append(lg)
+        return outs
+
+    def through(w, calls):
+        h, outs = None, []
+        for ids in calls:
+            _, lg, h = w(input_ids=ids, past_key_values=h)
+            outs.append(lg)
+        return outs
+
+    # (a) batch of two: prefill, two single-token steps, a two-token call
+    calls = [torch.tensor([[5, 17, 200], [9, 3, 4]]), torch.tensor([[7], [8]]), torch.tensor([[1], [2]]),
+             torch.tensor([[3, 4], [5, 6]])]
+    w = make()
+    for got, want in zip(through(w, calls), reference(calls)):
+        assert torch.equal(got, want)
+    assert w.n_valid == 7
+    # (b) prompt longer than the window: eager single-token steps, then a two-token call, then one more token
+    calls = [torch.arange(1, 13).reshape(1, 12), torch.tensor([[7]]), torch.tensor([[8]]), torch.tensor([[9, 10]]),
+             torch.tensor([[11]])]
+    w = make()
+    for got, want in zip(through(w, calls), reference(calls)):
+        assert torch.equal(got, want)
+    assert w.n_valid == 17
+    # (c) a handle from an earlier session is not accepted as the current cache
+    w = make()
+    _, _, old = w(input_ids=torch.arange(1, 13).reshape(1, 12), past_key_values=None)
+    _, _, new = w(input_ids=torch.arange(20, 32).reshape(1, 12), past_key_values=None)
+    _, lg_stale, _ = w(input_ids=torch.tensor([[7]]), past_key_values=old)      # == a fresh one-token prefill
+    assert torch.equal(lg_stale, reference([torch.tensor([[7]])])[0])

@@ -9,6 +9,10 @@
 //   chainbench steptrace [ctx]              fused step once with the in-kernel timeline of the linears
 //   chainbench program [reps]               the `chain` linears as ONE persistent launch (cgq_program_*),
 //                                           checked bit for bit against the launch-per-linear chain
+//   chainbench mk [reps]                    the `chain` linears as ONE launch of the step program (cgq_step_*, one
+//                                           fat CTA per SM, column slices), checked within the parity bar
+//   chainbench mkstep [ctx] [reps]          the FUSED token step (embedding, attention, linears) as one cgq_step_*
+//                                           launch against the 142-launch step; CGQ_STEP_TRACE=1 prints a timeline
 //
 // Weights are random bytes (nibbles 1..15), scales ~ 1/(4.4*sqrt(K)) so the chain stays finite.
 // Every timing is CUDA events around `reps` replays of a CUDA graph of the launches.
@@ -106,6 +110,23 @@ static void run_lin(const Lin& l, const __half* x, __half* y, int M, int lda, cu
                     st));
 }
 
+// elements of `got` outside |got - want| <= 1e-2 |want| + 1e-2 rms(want)
+static size_t count_outside(const std::vector<__half>& want, const std::vector<__half>& got, double* max_ratio) {
+  double ss = 0;
+  for (auto h : want) ss += (double)__half2float(h) * __half2float(h);
+  const double rms = sqrt(ss / want.size());
+  size_t bad = 0;
+  double worst = 0;
+  for (size_t i = 0; i < want.size(); ++i) {
+    const double w = __half2float(want[i]), g = __half2float(got[i]);
+    const double bound = 1e-2 * fabs(w) + 1e-2 * rms, err = fabs(g - w);
+    if (!(err <= bound)) ++bad;
+    worst = std::max(worst, err / std::max(bound, 1e-30));
+  }
+  if (max_ratio) *max_ratio = worst;
+  return bad;
+}
+
 static float time_graph(cudaGraphExec_t ge, cudaStream_t st, int reps) {
   for (int i = 0; i < 3; ++i) CK(cudaGraphLaunch(ge, st));
   CK(cudaStreamSynchronize(st));
@@ -164,8 +185,9 @@ int main(int argc, char** argv) {
     return 0;
   }
 
-  if (!strcmp(mode, "step") || !strcmp(mode, "steptrace")) {
+  if (!strcmp(mode, "step") || !strcmp(mode, "steptrace") || !strcmp(mode, "mkstep")) {
     const bool tracing = !strcmp(mode, "steptrace");
+    const bool mkstep = !strcmp(mode, "mkstep");
     int ctx = argc > 2 ? atoi(argv[2]) : 96;
     int reps = argc > 3 ? atoi(argv[3]) : 20;
     const int NH = 32, NG = 2, DH = 128, MAXLEN = ctx + 64;   // bench.py: prompt + generated + 32
@@ -236,6 +258,92 @@ int main(int argc, char** argv) {
     };
     step();
     CK(cudaStreamSynchronize(st));
+    if (mkstep) {
+      // the same token as ONE launch (cgq_step_*): logits against the launch-per-op step, determinism, timing
+      std::vector<__half> want(VOCAB), got(VOCAB), got2(VOCAB);
+      CK(cudaMemcpy(want.data(), logits, VOCAB * 2, cudaMemcpyDeviceToHost));
+      std::vector<cgq_step_op> ops;
+      auto lin = [&](size_t idx, const __half* a, __half* out, int pro, const __half* resid) {
+        const Lin& l = ls[idx];
+        cgq_step_op o;
+        memset(&o, 0, sizeof(o));
+        o.kind = CGQ_STEP_LINEAR; o.Wq = l.w; o.scale = l.s; o.bias = l.b; o.A = a; o.C = out; o.resid = resid;
+        o.norm_w = normw; o.N = l.N; o.K = l.K; o.prologue = pro; o.eps = 1e-5f;
+        ops.push_back(o);
+      };
+      {
+        cgq_step_op o;
+        memset(&o, 0, sizeof(o));
+        o.kind = CGQ_STEP_EMBED; o.Wq = emb.w; o.scale = emb.s; o.C = x; o.N = H; o.V = VOCAB; o.ids = ids;
+        ops.push_back(o);
+      }
+      for (int l = 0; l < LAYERS; ++l) {
+        lin(4 * l + 0, x, qkv, CGQ_PRO_RMSNORM, nullptr);
+        cgq_step_op o;
+        memset(&o, 0, sizeof(o));
+        o.kind = CGQ_STEP_ATTENTION; o.A = qkv; o.C = ao; o.freqs = freqs;
+        o.kcache = kc + (size_t)l * MAXLEN * NG * DH; o.vcache = vc + (size_t)l * MAXLEN * NG * DH;
+        o.n_head = NH; o.n_groups = NG; o.d_head = DH; o.max_len = MAXLEN;
+        ops.push_back(o);
+        lin(4 * l + 1, ao, x, CGQ_PRO_NONE, x);
+        lin(4 * l + 2, x, u, CGQ_PRO_RMSNORM, nullptr);
+        lin(4 * l + 3, u, x, CGQ_PRO_SILU_GATE, x);
+      }
+      lin(4 * LAYERS, x, logits, CGQ_PRO_RMSNORM, nullptr);
+      uint64_t h = 0;
+      CG(cgq_step_create(ops.data(), (int)ops.size(), CGQ_DTYPE_F16, state, &h));
+      for (int pass = 0; pass < 2; ++pass) {
+        CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(logits, 0, VOCAB * 2, st));
+        CG(cgq_step_run(h, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(pass ? got2.data() : got.data(), logits, VOCAB * 2, cudaMemcpyDeviceToHost));
+      }
+      int ctas = 0, stages = 0, failed = 0, pos[2];
+      CG(cgq_step_status(h, &ctas, &stages, &failed));
+      CK(cudaMemcpy(pos, state, 8, cudaMemcpyDeviceToHost));
+      double worst = 0;
+      const size_t bad = count_outside(want, got, &worst);
+      printf("mkstep: %zu ops in one launch, %d CTAs, %d ring stages, barrier failure flag %d, state[0] %d -> %d, logits outside the "
+             "1e-2 bar vs the launch-per-op step: %zu / %d (worst ratio %.3f), run-to-run identical: %s\n",
+             ops.size(), ctas, stages, failed, st0[0], pos[0], bad, VOCAB, worst,
+             memcmp(got.data(), got2.data(), VOCAB * 2) == 0 ? "yes" : "NO");
+      if (failed) return 2;
+      if (getenv("CGQ_STEP_TRACE")) {
+        uint64_t* tr;
+        const size_t words = ops.size() * (size_t)ctas;
+        CK(cudaMalloc(&tr, words * 8));
+        CK(cudaMemsetAsync(tr, 0, words * 8, st));
+        CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
+        cgq_debug_trace(tr);
+        CG(cgq_step_run(h, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<uint64_t> hh(words);
+        CK(cudaMemcpy(hh.data(), tr, words * 8, cudaMemcpyDeviceToHost));
+        const char* kinds[3] = {"linear", "attn", "embed"};
+        for (size_t op = 6; op <= 11 && op < ops.size(); ++op) {
+          uint64_t mn = ~0ull, mx = 0, pmn = ~0ull;
+          for (int c = 0; c < ctas; ++c) {
+            mn = std::min(mn, hh[op * ctas + c]); mx = std::max(mx, hh[op * ctas + c]);
+            pmn = std::min(pmn, hh[(op - 1) * ctas + c]);
+          }
+          printf("  barrier before op %zu (%s N=%d K=%d): previous phase took %.2f us, exit spread %.2f us\n", op,
+                 kinds[ops[op].kind], ops[op].N, ops[op].K, (mn - pmn) / 1e3, (mx - mn) / 1e3);
+        }
+      }
+      cudaGraph_t g;
+      cudaGraphExec_t ge;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      CG(cgq_step_run(h, st));
+      CK(cudaStreamEndCapture(st, &g));
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
+      float ms = time_graph(ge, st, reps);
+      CG(cgq_step_status(h, &ctas, &stages, &failed));
+      printf("mkstep ctx=%d..%d: %.1f us/token  %.1f tok/s  %.1f GB/s algorithmic linears (%.3f GB)  1 launch  (failure flag %d)\n",
+             ctx, ctx + reps + 3, ms * 1e3, 1e3 / ms, total / (ms * 1e-3) / 1e9, total / 1e9, failed);
+      return bad != 0 || failed;
+    }
     if (tracing) {
       CK(cudaMemset(trace, 0, sizeof(uint64_t) * kTraceWords * kTraceCtas * ls.size()));
       step();
@@ -301,7 +409,7 @@ int main(int argc, char** argv) {
 
   // ---- chain
   const bool program_mode = !strcmp(mode, "program");
-  int M = (argc > 2 && !program_mode) ? atoi(argv[2]) : 1;
+  int M = (argc > 2 && !program_mode && strcmp(mode, "mk")) ? atoi(argv[2]) : 1;
   int reps = program_mode ? (argc > 2 ? atoi(argv[2]) : 20) : (argc > 3 ? atoi(argv[3]) : 20);
   std::vector<Lin> ls;
   size_t total = 0;
@@ -323,6 +431,66 @@ int main(int argc, char** argv) {
   fill_h<<<64, 256>>>(x, (size_t)M * H, 5, -1.f, 1.f);
   CK(cudaDeviceSynchronize());
 
+  if (!strcmp(mode, "mk")) {
+    // the chain's linears as ONE launch (cgq_step_*, linears only) against one launch per linear
+    struct Step { const Lin* l; const __half* in; __half* out; };
+    __half* xa;
+    CK(cudaMalloc(&xa, (size_t)H * 2));
+    std::vector<Step> steps;
+    const __half* in = x;
+    for (int l = 0; l < LAYERS; ++l) {
+      const Lin* p = &ls[4 * l];
+      __half* out = (l & 1) ? xa : b3;
+      steps.push_back({&p[0], in, b0});
+      steps.push_back({&p[1], b0, b1});
+      steps.push_back({&p[2], b1, b2});
+      steps.push_back({&p[3], b2, out});
+      in = out;
+    }
+    steps.push_back({&ls.back(), in, logits});
+    if (getenv("CGQ_DBG_OPS")) steps.resize(std::min<size_t>(steps.size(), atoi(getenv("CGQ_DBG_OPS"))));
+    const int n_out = steps.back().l->N;
+    reps = argc > 2 ? atoi(argv[2]) : 20;
+    for (auto& sp : steps) run_lin(*sp.l, sp.in, sp.out, 1, sp.l->K, st);
+    CK(cudaStreamSynchronize(st));
+    std::vector<__half> want(n_out), got(n_out), got2(n_out);
+    CK(cudaMemcpy(want.data(), steps.back().out, n_out * 2, cudaMemcpyDeviceToHost));
+    std::vector<cgq_step_op> ops;
+    for (auto& sp : steps) {
+      cgq_step_op o;
+      memset(&o, 0, sizeof(o));
+      o.kind = CGQ_STEP_LINEAR; o.Wq = sp.l->w; o.scale = sp.l->s; o.bias = sp.l->b; o.A = sp.in; o.C = sp.out;
+      o.N = sp.l->N; o.K = sp.l->K; o.prologue = CGQ_PRO_NONE;
+      ops.push_back(o);
+    }
+    uint64_t h = 0;
+    CG(cgq_step_create(ops.data(), (int)ops.size(), CGQ_DTYPE_F16, nullptr, &h));
+    for (int pass = 0; pass < 2; ++pass) {
+      CK(cudaMemsetAsync(steps.back().out, 0, n_out * 2, st));
+      CG(cgq_step_run(h, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaMemcpy(pass ? got2.data() : got.data(), steps.back().out, n_out * 2, cudaMemcpyDeviceToHost));
+    }
+    int ctas = 0, stages = 0, failed = 0;
+    CG(cgq_step_status(h, &ctas, &stages, &failed));
+    double worst = 0;
+    const size_t bad = count_outside(want, got, &worst);
+    printf("mk: %zu linears in one launch, %d CTAs, %d ring stages, barrier failure flag %d, outputs outside the 1e-2 bar vs the "
+           "launch-per-linear chain: %zu / %d (worst ratio %.3f), run-to-run identical: %s\n",
+           ops.size(), ctas, stages, failed, bad, n_out, worst, memcmp(got.data(), got2.data(), n_out * 2) == 0 ? "yes" : "NO");
+    if (failed) return 2;
+    cudaGraph_t g;
+    cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    CG(cgq_step_run(h, st));
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    float ms = time_graph(ge, st, reps);
+    CG(cgq_step_status(h, &ctas, &stages, &failed));
+    printf("mk M=1: %.1f us/token  %.1f tok/s  %.1f GB/s algorithmic (%.3f GB)  1 launch, %zu linears  (failure flag %d)\n",
+           ms * 1e3, 1e3 / ms, total / (ms * 1e-3) / 1e9, total / 1e9, ops.size(), failed);
+    return bad != 0;
+  }
   if (program_mode) {
     // the chain as (linear, input, output) steps; ping-pong hidden-state buffers so that no step overwrites
     // its own input
