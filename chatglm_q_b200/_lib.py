@@ -63,13 +63,14 @@ class LinearOp(ctypes.Structure):
 
 
 STEP_LINEAR, STEP_ATTENTION, STEP_EMBED = 0, 1, 2
+EPI_NONE, EPI_SILU_PAIR = 0, 1
 
 
 class StepOp(ctypes.Structure):
     """`cgq_step_op` of include/cgq.h (one phase of the one-launch decode step)."""
     _fields_ = [("kind", c_int), ("Wq", c_void_p), ("scale", c_void_p), ("bias", c_void_p), ("A", c_void_p),
                 ("C", c_void_p), ("resid", c_void_p), ("norm_w", c_void_p), ("N", c_int), ("K", c_int),
-                ("prologue", c_int), ("eps", c_float), ("freqs", c_void_p), ("kcache", c_void_p), ("vcache", c_void_p),
+                ("prologue", c_int), ("eps", c_float), ("epilogue", c_int), ("freqs", c_void_p), ("kcache", c_void_p), ("vcache", c_void_p),
                 ("n_head", c_int), ("n_groups", c_int), ("d_head", c_int), ("max_len", c_int), ("ids", c_void_p),
                 ("V", c_int)]
 

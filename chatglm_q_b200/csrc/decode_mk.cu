@@ -47,7 +47,10 @@ constexpr int kTeams = 4;
 constexpr int kTeamWarps = 4;
 constexpr int kConsWarps = kTeams * kTeamWarps;
 constexpr int kCons = kConsWarps * 32;            // 512 consumer threads
-constexpr int kMkThreads = kCons + 32;            // + producer warp
+constexpr int kEpiWarp = kConsWarps;              // warp 16: slice epilogues (reduction, rounding, stores, TP exchange)
+constexpr int kProdWarp = kConsWarps + 1;         // warp 17: TMA producer
+constexpr int kSyncThreads = kCons + 32;          // consumers + epilogue warp meet in the grid barrier
+constexpr int kMkThreads = kCons + 64;
 constexpr int kWBytes = 8192, kSBytes = 1024;     // one ring stage: packed weights + scales
 constexpr int kMaxBandK = 13824;                  // activation row capacity (k), multiple of every stage depth
 constexpr int kBandBytes = kMaxBandK * 2;
@@ -55,6 +58,7 @@ constexpr int kGsumBytes = (kMaxBandK / 32) * 4;
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 
 enum { OP_LINEAR = CGQ_STEP_LINEAR, OP_ATTENTION = CGQ_STEP_ATTENTION, OP_EMBED = CGQ_STEP_EMBED };
+enum { EPI_NONE = CGQ_EPI_NONE, EPI_SILU_PAIR = CGQ_EPI_SILU_PAIR };
 
 template <int BW>
 struct Geo {
@@ -84,23 +88,30 @@ struct alignas(128) MkOp {
   int kind, N, K, slices, spk, prologue;
   float eps;
   int n_head, n_groups, max_len, V;
+  int epi;       // EPI_SILU_PAIR: column n of the first half and of the second half are one CTA's consecutive slices
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void cons_sync() { ptx::named_bar_sync(1, kCons); }
+// slice sequence of CTA w for op o: (p, hh) -> slice index; EPI_SILU_PAIR walks (h slice p, gate slice p) pairs
+struct SliceIter {
+  int per, pairs;
+  __device__ __forceinline__ explicit SliceIter(const MkOp& o)
+      : per(o.epi == EPI_SILU_PAIR ? o.slices / 2 : o.slices), pairs(o.epi == EPI_SILU_PAIR ? 2 : 1) {}
+};
 
-// All consumer warps of all CTAs meet here between two dependent phases; the producer warps never do.
+__device__ __forceinline__ void cons_sync() { ptx::named_bar_sync(2, kCons); }          // the 16 consumer warps
+__device__ __forceinline__ void step_sync() { ptx::named_bar_sync(1, kSyncThreads); }  // + the epilogue warp
+
+// Consumer warps and the epilogue warp of all CTAs meet here between two dependent phases; the producer warps
+// never do.  One release-add per CTA, relaxed polling (one L2 round trip per poll) and a single acquire fence.
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, unsigned long long* trace, int op) {
-  cons_sync();                                    // this CTA's global stores are issued
+  step_sync();                                    // this CTA's global stores are issued
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
-    unsigned spins = 0;
+    unsigned spins = 0, v;
     volatile unsigned* failed = ctr + 1;
-    while (ld_acquire_gpu(ctr) < target) {
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
       // a CTA is missing (seconds have passed): give up loudly instead of hanging the device; sticky flag,
       // later barriers fall through at once and cgq_step_status reports it
       if (++spins > (1u << 24) || *failed != 0) {
@@ -108,13 +119,14 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, uns
         break;
       }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     if (trace != nullptr) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       trace[static_cast<size_t>(op) * gridDim.x + blockIdx.x] = t;
     }
   }
-  cons_sync();
+  step_sync();
 }
 
 // 8 activations (k = 8c .. 8c+7) -> two B-fragment units [ (a0,a2), (a1,a3)*2^-4, (a4,a6), (a5,a7)*2^-4 ] and
@@ -231,13 +243,15 @@ __device__ __forceinline__ void consume_stage(uint32_t wst, uint32_t sst, uint32
   }
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
   float grp[G::GP][G::CC][4];
+  // (the MMAs are volatile asm and issue in source order: the two dependent MMAs of a (group, chunk) tile pair are
+  // kept 8 MMAs apart -- back to back they stall ~30 cycles each on the accumulator)
 #pragma unroll
-  for (int gp = 0; gp < G::GP; ++gp) {
+  for (int h = 0; h < 2; ++h) {                     // the two row tiles (16 k each) of a group
 #pragma unroll
-    for (int cc = 0; cc < G::CC; ++cc) {
-      const int i = gp * (G::CC / 2) + (cc >> 1);
+    for (int gp = 0; gp < G::GP; ++gp) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {                 // the two row tiles (16 k each) of the group
+      for (int cc = 0; cc < G::CC; ++cc) {
+        const int i = gp * (G::CC / 2) + (cc >> 1);
         const uint32_t x = w[i][h + 2 * (cc & 1)];
         const uint32_t z = x >> 8;
         const uint32_t a[4] = {x & 0x000F000Fu, z & 0x000F000Fu, x & 0x00F000F0u, z & 0x00F000F0u};
@@ -439,6 +453,13 @@ __device__ __forceinline__ void attention_head(const MkOp& o, int h, int n_past,
 }
 
 // ============================================================================================ the kernel
+// SwiGLU of one element, the reference's roundings (model.py:200-201; same fast exp / divide as w4::silu_gate8)
+__device__ __forceinline__ __half silu_mul(__half h, __half gate) {
+  const float x = __half2float(h);
+  const __half act = __float2half_rn(__fdividef(x, 1.f + __expf(-x)));
+  return __float2half_rn(__half2float(act) * __half2float(gate));
+}
+
 template <int BW>
 __global__ void __launch_bounds__(kMkThreads, 1)
     w4_step_kernel(const MkOp* __restrict__ ops, int n_ops, int S, unsigned* __restrict__ ctr, int* __restrict__ state,
@@ -455,7 +476,9 @@ __global__ void __launch_bounds__(kMkThreads, 1)
   float* band_f = reinterpret_cast<float*>(gen + off_band);               // attention scratch aliases the band
   float* gsum = reinterpret_cast<float*>(gen + off_band + kBandBytes);
   float* red = reinterpret_cast<float*>(gen + off_band + kBandBytes + kGsumBytes);
-  float* sred = reinterpret_cast<float*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES);   // [32]
+  float* sred = reinterpret_cast<float*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES);   // [16]
+  uint64_t* red_full = reinterpret_cast<uint64_t*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES + 64);  // [2]
+  uint64_t* red_empty = red_full + 2;                                                                           // [2]
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES + 128);
   uint64_t* empty = full + S;
 
@@ -466,11 +489,16 @@ __global__ void __launch_bounds__(kMkThreads, 1)
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], kTeamWarps);
     }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&red_full[b], kConsWarps);
+      ptx::mbar_init(&red_empty[b], 1);
+    }
     ptx::fence_mbar_init();
   }
+  __syncwarp();
   __syncthreads();
 
-  if (warp == kConsWarps) {
+  if (warp == kProdWarp) {
     // =========================== producer: one lane walks the whole step ===========================
     if (lane == 0) {
       const uint64_t pol = ptx::policy_evict_first();
@@ -478,16 +506,64 @@ __global__ void __launch_bounds__(kMkThreads, 1)
       for (int op = 0; op < n_ops; ++op) {
         const MkOp* o = ops + op;
         if (o->kind != OP_LINEAR) continue;
-        const int slices = o->slices, spk = o->spk;
-        for (int sl = w; sl < slices; sl += W) {
-          for (int u = 0; u < spk; ++u) {
-            const int slot = issued % S;
-            if (issued >= static_cast<unsigned>(S)) ptx::mbar_wait(&empty[slot], ((issued / S) - 1) & 1);
-            ptx::mbar_expect_tx(&full[slot], kWBytes + kSBytes);
-            ptx::tma_load_2d(gen + slot * kWBytes, &o->tmW, sl * BW, u * G::ROWS, &full[slot], pol);
-            ptx::tma_load_2d(gen + S * kWBytes + slot * kSBytes, &o->tmS, sl * BW, u * (G::ROWS / 16), &full[slot], pol);
-            ++issued;
+        const SliceIter it(*o);
+        const int spk = o->spk;
+        for (int p = w; p < it.per; p += W) {
+          for (int hh = 0; hh < it.pairs; ++hh) {
+            const int sl = p + hh * it.per;
+            for (int u = 0; u < spk; ++u) {
+              const int slot = issued % S;
+              if (issued >= static_cast<unsigned>(S)) ptx::mbar_wait(&empty[slot], ((issued / S) - 1) & 1);
+              ptx::mbar_expect_tx(&full[slot], kWBytes + kSBytes);
+              ptx::tma_load_2d(gen + slot * kWBytes, &o->tmW, sl * BW, u * G::ROWS, &full[slot], pol);
+              ptx::tma_load_2d(gen + S * kWBytes + slot * kSBytes, &o->tmS, sl * BW, u * (G::ROWS / 16), &full[slot], pol);
+              ++issued;
+            }
           }
+        }
+      }
+    }
+    return;
+  }
+
+  if (warp == kEpiWarp) {
+    // =========================== epilogue warp ===========================
+    // Sums the 16 consumer warps' partial columns of a finished slice (fixed order), rounds, adds bias / residual
+    // and stores -- while the consumer warps are already in the next slice.  Joins every grid barrier.
+    unsigned eseq = 0;
+    for (int op = 0; op < n_ops; ++op) {
+      if (op > 0) grid_barrier(ctr, static_cast<unsigned>(op) * W, nullptr, op);
+      const MkOp& o = ops[op];
+      if (o.kind != OP_LINEAR) continue;
+      const SliceIter it(o);
+      const T* bias = static_cast<const T*>(o.bias);
+      const T* resid = static_cast<const T*>(o.resid);
+      T* C = static_cast<T*>(o.C);
+      for (int p = w; p < it.per; p += W) {
+        T keep[BW / 32];
+        for (int hh = 0; hh < it.pairs; ++hh, ++eseq) {
+          const int sl = p + hh * it.per, buf = eseq & 1;
+          ptx::mbar_wait(&red_full[buf], (eseq >> 1) & 1);
+          const float* rb = red + buf * (kConsWarps * BW);
+#pragma unroll
+          for (int j = 0; j < BW / 32; ++j) {
+            const int c = lane + 32 * j;
+            float acc = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kConsWarps; ++ww) acc += rb[ww * BW + c];
+            const int n = sl * BW + c;
+            if (o.epi == EPI_SILU_PAIR) {
+              const T v = epilogue<T>(acc, bias, n);
+              if (hh == 0)
+                keep[j] = v;                                             // h, rounded like w_in's output
+              else
+                C[p * BW + c] = silu_mul(keep[j], v);                    // u = silu(h) * gate
+            } else if (n < o.N) {
+              C[n] = w4::add_resid<T>(epilogue<T>(acc, bias, n), resid, n);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&red_empty[buf]);
         }
       }
     }
@@ -513,8 +589,7 @@ __global__ void __launch_bounds__(kMkThreads, 1)
       ld_off[i] = static_cast<uint32_t>(r * BW + ((cc ^ ((r >> G::SWSH) & G::SWMASK)) << 4));
     }
   }
-  unsigned seen = 0;
-  int redbuf = 0;
+  unsigned seen = 0, sseq = 0;
   for (int op = 0; op < n_ops; ++op) {
     const MkOp& o = ops[op];
     if (op > 0) {
@@ -543,41 +618,37 @@ __global__ void __launch_bounds__(kMkThreads, 1)
       continue;
     }
     // ---- linear
-    const int slices = o.slices, spk = o.spk;
-    if (w >= slices) continue;
+    const SliceIter it(o);
+    const int spk = o.spk;
+    if (w >= it.per) continue;
     stage_activation<BW>(o, Aband, gsum, sred);
     const uint32_t rt_zero = static_cast<uint32_t>(o.K) >> 31;
-    for (int sl = w; sl < slices; sl += W) {
-      float tot[G::CC][2];
+    for (int p = w; p < it.per; p += W) {
+      for (int hh = 0; hh < it.pairs; ++hh, ++sseq) {
+        float tot[G::CC][2];
 #pragma unroll
-      for (int cc = 0; cc < G::CC; ++cc) tot[cc][0] = tot[cc][1] = 0.f;
-      for (int u = 0; u < spk; ++u, ++seen) {
-        if (static_cast<int>(seen % kTeams) != team) continue;
-        const int slot = seen % S;
-        ptx::mbar_wait(&full[slot], (seen / S) & 1);
-        consume_stage<BW>(Wsm + slot * kWBytes, Ssm + slot * kSBytes, Aband, gsum, u, ld_off, wq, g, tig, &empty[slot],
-                          rt_zero, tot);
-      }
-      // ---- the 16 warps' partial sums of this slice meet in shared memory (fixed order: deterministic)
-      float* rb = red + redbuf * (kConsWarps * BW);
-      if (tig == 0) {
-#pragma unroll
-        for (int cc = 0; cc < G::CC; ++cc) {
-          rb[warp * BW + 16 * cc + 2 * g] = tot[cc][0];
-          rb[warp * BW + 16 * cc + 2 * g + 1] = tot[cc][1];
+        for (int cc = 0; cc < G::CC; ++cc) tot[cc][0] = tot[cc][1] = 0.f;
+        for (int u = 0; u < spk; ++u, ++seen) {
+          if (static_cast<int>(seen % kTeams) != team) continue;
+          const int slot = seen % S;
+          ptx::mbar_wait(&full[slot], (seen / S) & 1);
+          consume_stage<BW>(Wsm + slot * kWBytes, Ssm + slot * kSBytes, Aband, gsum, u, ld_off, wq, g, tig, &empty[slot],
+                            rt_zero, tot);
         }
-      }
-      cons_sync();
-      if (tid < BW) {
-        float acc = 0.f;
+        // ---- hand the warp's partial columns of this slice to the epilogue warp (double-buffered)
+        const int buf = sseq & 1;
+        if (sseq >= 2) ptx::mbar_wait(&red_empty[buf], ((sseq >> 1) - 1) & 1);
+        float* rb = red + buf * (kConsWarps * BW);
+        if (tig == 0) {
 #pragma unroll
-        for (int ww = 0; ww < kConsWarps; ++ww) acc += rb[ww * BW + tid];
-        const int n = sl * BW + tid;
-        if (n < o.N)
-          static_cast<T*>(o.C)[n] = w4::add_resid<T>(epilogue<T>(acc, static_cast<const T*>(o.bias), n),
-                                                     static_cast<const T*>(o.resid), n);
+          for (int cc = 0; cc < G::CC; ++cc) {
+            rb[warp * BW + 16 * cc + 2 * g] = tot[cc][0];
+            rb[warp * BW + 16 * cc + 2 * g + 1] = tot[cc][1];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&red_full[buf]);
       }
-      redbuf ^= 1;
     }
   }
 }
@@ -703,6 +774,12 @@ extern "C" int cgq_step_create(const cgq_step_op* ops, int n_ops, int dtype, int
       d.K = s.K;
       d.prologue = s.prologue;
       d.eps = s.eps;
+      d.epi = s.epilogue;
+      if (s.epilogue != CGQ_EPI_NONE && (s.epilogue != CGQ_EPI_SILU_PAIR || s.N % (2 * BW) != 0 || s.resid != nullptr)) {
+        set_error("%s: op %d: bad epilogue %d (CGQ_EPI_SILU_PAIR needs N a multiple of %d and no residual)", fn, i,
+                  s.epilogue, 2 * BW);
+        return CGQ_ERR_BAD_SHAPE;
+      }
       d.slices = s.N / BW;
       d.spk = (s.K / 2 + rows - 1) / rows;
       const int swz = BW == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (BW == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   const int n_units = u1 - u0;
   const T* A = static_cast<const T*>(p.A);
 
-  if (threadIdx.x == 0) stamp(p, 0);
   // ---- prologue: barriers
   if (threadIdx.x == CW * 32) {
     ptx::prefetch_tmap(&tmW);
@@ -220,8 +219,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     }
     ptx::fence_mbar_init();
   }
-  __syncwarp();      // (the single-thread branches above must have reconverged before the aligned block barrier)
+  __syncwarp();      // (the single-thread branch above must have reconverged before the aligned block barrier)
   __syncthreads();
+  if (threadIdx.x == 0) stamp(p, 0);
   // Distributed shared memory may only be written once the target CTA is known to run: every CTA of the cluster
   // arrives here (non-blocking) and waits right before its first remote store (compute-sanitizer racecheck:
   // "block that might not have entered yet").  Free in practice -- the cluster is co-scheduled.

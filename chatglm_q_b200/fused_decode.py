@@ -183,14 +183,14 @@ class FusedDecodeModel:
         cfg, m = self.cfg, self.model
         ops = []
 
-        def lin(l, a, out, pro=PRO_NONE, norm=None, resid=None):
+        def lin(l, a, out, pro=PRO_NONE, norm=None, resid=None, epi=0):
             k2, n = l.weight.shape
             bias = getattr(l, "bias", None)
             ops.append(StepOp(kind=STEP_LINEAR, Wq=l.weight.data_ptr(), scale=l.weight_scale.data_ptr(),
                               bias=None if bias is None else bias.data_ptr(), A=a.data_ptr(), C=out.data_ptr(),
                               resid=None if resid is None else resid.data_ptr(),
                               norm_w=None if norm is None else norm.weight.data_ptr(), N=n, K=2 * k2, prologue=pro,
-                              eps=float(norm.eps) if norm is not None else 0.0))
+                              eps=float(norm.eps) if norm is not None else 0.0, epilogue=epi))
 
         emb = m.word_embedding
         ops.append(StepOp(kind=STEP_EMBED, Wq=emb.weight.data_ptr(), scale=emb.weight_scale.data_ptr(),
@@ -201,8 +201,9 @@ class FusedDecodeModel:
                               kcache=kc.data_ptr(), vcache=vc.data_ptr(), n_head=cfg.num_attention_heads,
                               n_groups=cfg.num_multi_query_groups, d_head=cfg.head_hidden_size, max_len=self.max_len))
             lin(layer.attn.o_proj, self.ao, self.x, resid=self.x)
-            lin(layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln)
-            lin(layer.ffn.w_out, self.u, self.x, PRO_SILU_GATE, resid=self.x)
+            # silu(h) * gate is applied once, in w_in's epilogue (u holds inner_hidden_size values)
+            lin(layer.ffn.w_in, self.x, self.u, PRO_RMSNORM, layer.ffn_ln, epi=_lib.EPI_SILU_PAIR)
+            lin(layer.ffn.w_out, self.u, self.x, PRO_NONE, resid=self.x)
         lin(m.lm_head, self.x, self.logits, PRO_RMSNORM, m.final_ln)
         arr = (StepOp * len(ops))(*ops)
         handle = ctypes.c_uint64(0)

@@ -225,6 +225,11 @@ int cgq_program_destroy(uint64_t handle);
 #define CGQ_STEP_LINEAR 0
 #define CGQ_STEP_ATTENTION 1
 #define CGQ_STEP_EMBED 2
+/* LINEAR epilogues.  CGQ_EPI_SILU_PAIR (w_in, model.py:200-201): the N columns are [h | gate]; the op stores
+ * C[N/2] = round(round(silu(round(h))) * round(gate)) instead of the N raw outputs, so that the next linear (w_out)
+ * takes it with CGQ_PRO_NONE -- the same roundings as CGQ_PRO_SILU_GATE on the raw outputs, computed once. */
+#define CGQ_EPI_NONE 0
+#define CGQ_EPI_SILU_PAIR 1
 typedef struct {
   int kind;             /* CGQ_STEP_* */
   const uint8_t* Wq;    /* LINEAR: [K/2, N]; EMBED: [V/2, N] */
@@ -237,6 +242,7 @@ typedef struct {
   int N, K;             /* EMBED: N = embedding dim */
   int prologue;         /* CGQ_PRO_* */
   float eps;
+  int epilogue;         /* CGQ_EPI_* */
   const void* freqs;    /* ATTENTION: rotary table [max_pos, d_head] */
   void* kcache;         /* ATTENTION: [max_len, n_groups, d_head] */
   void* vcache;

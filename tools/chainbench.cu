@@ -287,7 +287,12 @@ int main(int argc, char** argv) {
         ops.push_back(o);
         lin(4 * l + 1, ao, x, CGQ_PRO_NONE, x);
         lin(4 * l + 2, x, u, CGQ_PRO_RMSNORM, nullptr);
-        lin(4 * l + 3, u, x, CGQ_PRO_SILU_GATE, x);
+        if (!getenv("CGQ_STEP_NO_PAIR")) {
+          ops.back().epilogue = CGQ_EPI_SILU_PAIR;     // silu(h) * gate in w_in's epilogue, w_out reads u[13696]
+          lin(4 * l + 3, u, x, CGQ_PRO_NONE, x);
+        } else {
+          lin(4 * l + 3, u, x, CGQ_PRO_SILU_GATE, x);
+        }
       }
       lin(4 * LAYERS, x, logits, CGQ_PRO_RMSNORM, nullptr);
       uint64_t h = 0;
