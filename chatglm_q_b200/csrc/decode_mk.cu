@@ -98,12 +98,32 @@ struct SliceIter {
       : per(o.epi == EPI_SILU_PAIR ? o.slices / 2 : o.slices), pairs(o.epi == EPI_SILU_PAIR ? 2 : 1) {}
 };
 
+// optional in-kernel timeline (cgq_debug_trace): 8 stamps per (op, CTA):
+//   0 barrier passed   1 activation staged   2 first stage consumed (warp 0)   3 last stage consumed (warp 0)
+//   4 last stage consumed (warp 15)   5 last slice stored (epilogue warp)   6 arrived at the next barrier
+constexpr int kTraceSlots = 8;
+__device__ __forceinline__ void stamp(unsigned long long* trace, int op, int slot) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(static_cast<size_t>(op) * gridDim.x + blockIdx.x) * kTraceSlots + slot] = t;
+  }
+}
 __device__ __forceinline__ void cons_sync() { ptx::named_bar_sync(2, kCons); }          // the 16 consumer warps
 __device__ __forceinline__ void step_sync() { ptx::named_bar_sync(1, kSyncThreads); }  // + the epilogue warp
+// slice hand-off consumers -> epilogue warp, double-buffered, on hardware named barriers (3 + buf: partial columns
+// written; 5 + buf: buffer free again): the writers `bar.arrive`, the reader `bar.sync`, and vice versa
+__device__ __forceinline__ void bar_arrive(int id) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kSyncThreads) : "memory");
+}
+__device__ __forceinline__ void bar_wait(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kSyncThreads) : "memory");
+}
 
 // Consumer warps and the epilogue warp of all CTAs meet here between two dependent phases; the producer warps
 // never do.  One release-add per CTA, relaxed polling (one L2 round trip per poll) and a single acquire fence.
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, unsigned long long* trace, int op) {
+  if (threadIdx.x == 0 && op > 0) stamp(trace, op - 1, 6);
   step_sync();                                    // this CTA's global stores are issued
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
@@ -120,11 +140,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, uns
       }
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    if (trace != nullptr) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      trace[static_cast<size_t>(op) * gridDim.x + blockIdx.x] = t;
-    }
+    stamp(trace, op, 0);
   }
   step_sync();
 }
@@ -221,7 +237,8 @@ __device__ __forceinline__ void stage_activation(const MkOp& o, uint32_t Aband, 
 template <int BW>
 __device__ __forceinline__ void consume_stage(uint32_t wst, uint32_t sst, uint32_t Aband, const float* gsum, int u,
                                               const uint32_t (&ld_off)[4], int wq, int g, int tig,
-                                              uint64_t* empty_bar, uint32_t rt_zero, float (&tot)[Geo<BW>::CC][2]) {
+                                              uint64_t* empty_bar, uint32_t rt_zero, float (&tot)[Geo<BW>::CC][2],
+                                              int dbg) {
   using G = Geo<BW>;
   using T = __half;
   const int lane = threadIdx.x & 31;
@@ -245,6 +262,12 @@ __device__ __forceinline__ void consume_stage(uint32_t wst, uint32_t sst, uint32
   float grp[G::GP][G::CC][4];
   // (the MMAs are volatile asm and issue in source order: the two dependent MMAs of a (group, chunk) tile pair are
   // kept 8 MMAs apart -- back to back they stall ~30 cycles each on the accumulator)
+  if (dbg & 1) {      // diagnosis only (CGQ_STEP_DBG=1): no unpack / MMA work, everything else unchanged
+#pragma unroll
+    for (int gp = 0; gp < G::GP; ++gp)
+#pragma unroll
+      for (int cc = 0; cc < G::CC; ++cc) grp[gp][cc][0] = grp[gp][cc][2] = __uint_as_float(w[gp % 4][cc % 4]);
+  } else
 #pragma unroll
   for (int h = 0; h < 2; ++h) {                     // the two row tiles (16 k each) of a group
 #pragma unroll
@@ -463,7 +486,7 @@ __device__ __forceinline__ __half silu_mul(__half h, __half gate) {
 template <int BW>
 __global__ void __launch_bounds__(kMkThreads, 1)
     w4_step_kernel(const MkOp* __restrict__ ops, int n_ops, int S, unsigned* __restrict__ ctr, int* __restrict__ state,
-                   unsigned long long* __restrict__ trace) {
+                   unsigned long long* __restrict__ trace, int dbg) {
   using G = Geo<BW>;
   using T = __half;
   extern __shared__ uint8_t smem_raw[];
@@ -477,8 +500,6 @@ __global__ void __launch_bounds__(kMkThreads, 1)
   float* gsum = reinterpret_cast<float*>(gen + off_band + kBandBytes);
   float* red = reinterpret_cast<float*>(gen + off_band + kBandBytes + kGsumBytes);
   float* sred = reinterpret_cast<float*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES);   // [16]
-  uint64_t* red_full = reinterpret_cast<uint64_t*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES + 64);  // [2]
-  uint64_t* red_empty = red_full + 2;                                                                           // [2]
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_band + kBandBytes + kGsumBytes + G::RED_BYTES + 128);
   uint64_t* empty = full + S;
 
@@ -488,10 +509,6 @@ __global__ void __launch_bounds__(kMkThreads, 1)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], kTeamWarps);
-    }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&red_full[b], kConsWarps);
-      ptx::mbar_init(&red_empty[b], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -523,16 +540,13 @@ __global__ void __launch_bounds__(kMkThreads, 1)
         }
       }
     }
-    return;
-  }
-
-  if (warp == kEpiWarp) {
+  } else if (warp == kEpiWarp) {
     // =========================== epilogue warp ===========================
     // Sums the 16 consumer warps' partial columns of a finished slice (fixed order), rounds, adds bias / residual
     // and stores -- while the consumer warps are already in the next slice.  Joins every grid barrier.
     unsigned eseq = 0;
     for (int op = 0; op < n_ops; ++op) {
-      if (op > 0) grid_barrier(ctr, static_cast<unsigned>(op) * W, nullptr, op);
+      if (op > 0) grid_barrier(ctr, static_cast<unsigned>(op) * W, trace, op);
       const MkOp& o = ops[op];
       if (o.kind != OP_LINEAR) continue;
       const SliceIter it(o);
@@ -543,7 +557,7 @@ __global__ void __launch_bounds__(kMkThreads, 1)
         T keep[BW / 32];
         for (int hh = 0; hh < it.pairs; ++hh, ++eseq) {
           const int sl = p + hh * it.per, buf = eseq & 1;
-          ptx::mbar_wait(&red_full[buf], (eseq >> 1) & 1);
+          bar_wait(3 + buf);
           const float* rb = red + buf * (kConsWarps * BW);
 #pragma unroll
           for (int j = 0; j < BW / 32; ++j) {
@@ -562,14 +576,12 @@ __global__ void __launch_bounds__(kMkThreads, 1)
               C[n] = w4::add_resid<T>(epilogue<T>(acc, bias, n), resid, n);
             }
           }
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&red_empty[buf]);
+          bar_arrive(5 + buf);
         }
       }
+      if (lane == 0) stamp(trace, op, 5);
     }
-    return;
-  }
-
+  } else {
   // =========================== consumers ===========================
   const int tid = threadIdx.x;
   const int team = warp / kTeamWarps, wq = warp % kTeamWarps;
@@ -621,7 +633,9 @@ __global__ void __launch_bounds__(kMkThreads, 1)
     const SliceIter it(o);
     const int spk = o.spk;
     if (w >= it.per) continue;
-    stage_activation<BW>(o, Aband, gsum, sred);
+    if (!(dbg & 2)) stage_activation<BW>(o, Aband, gsum, sred);     // (CGQ_STEP_DBG=2: diagnosis, no prologue)
+    if (tid == 0) stamp(trace, op, 1);
+    bool first_done = false;
     const uint32_t rt_zero = static_cast<uint32_t>(o.K) >> 31;
     for (int p = w; p < it.per; p += W) {
       for (int hh = 0; hh < it.pairs; ++hh, ++sseq) {
@@ -633,11 +647,13 @@ __global__ void __launch_bounds__(kMkThreads, 1)
           const int slot = seen % S;
           ptx::mbar_wait(&full[slot], (seen / S) & 1);
           consume_stage<BW>(Wsm + slot * kWBytes, Ssm + slot * kSBytes, Aband, gsum, u, ld_off, wq, g, tig, &empty[slot],
-                            rt_zero, tot);
+                            rt_zero, tot, dbg);
+          if (trace != nullptr && !first_done && tid == 0) stamp(trace, op, 2);
+          first_done = true;
         }
         // ---- hand the warp's partial columns of this slice to the epilogue warp (double-buffered)
         const int buf = sseq & 1;
-        if (sseq >= 2) ptx::mbar_wait(&red_empty[buf], ((sseq >> 1) - 1) & 1);
+        if (sseq >= 2) bar_wait(5 + buf);
         float* rb = red + buf * (kConsWarps * BW);
         if (tig == 0) {
 #pragma unroll
@@ -646,11 +662,15 @@ __global__ void __launch_bounds__(kMkThreads, 1)
             rb[warp * BW + 16 * cc + 2 * g + 1] = tot[cc][1];
           }
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&red_full[buf]);
+        bar_arrive(3 + buf);
       }
     }
+    if (lane == 0 && warp == 0) stamp(trace, op, 3);
+    if (lane == 0 && warp == kConsWarps - 1) stamp(trace, op, 4);
   }
+  }  // consumers
+  // (no warp leaves early: every role falls through to here, which keeps the named barriers' thread sets intact
+  // for compute-sanitizer's synccheck)
 }
 
 // ------------------------------------------------------------------ host: step objects
@@ -704,8 +724,12 @@ int launch_step(const Step& st, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CGQ_CUDA_TRY(cudaMemsetAsync(st.d_ctr, 0, 2 * sizeof(unsigned), stream));
+  static const int dbg = [] {
+    const char* s = getenv("CGQ_STEP_DBG");       // diagnosis switches (wrong results): 1 no MMA work, 2 no prologue
+    return s != nullptr ? atoi(s) : 0;
+  }();
   CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, static_cast<const MkOp*>(st.d_ops), st.n_ops, st.stages, st.d_ctr,
-                                  st.state, static_cast<unsigned long long*>(take_trace_buffer())));
+                                  st.state, static_cast<unsigned long long*>(take_trace_buffer()), dbg));
   return CGQ_OK;
 }
 

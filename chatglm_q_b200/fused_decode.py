@@ -56,7 +56,8 @@ def _is_w4_linear(m) -> bool:
 
 class FusedDecodeModel:
     def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None,
-                 speculate: bool = False, last_logits_only: bool = False, alias_logits: bool | None = None):
+                 speculate: bool = False, last_logits_only: bool = False, alias_logits: bool | None = None,
+                 one_launch: bool | None = None):
         cfg = model.config
         # The fused step writes its logits into ONE static buffer.  The reference returns a fresh tensor per call, so
         # by default the wrapper hands out a copy (130 KB); `alias_logits=True` returns the static buffer itself (it is
@@ -66,9 +67,14 @@ class FusedDecodeModel:
         if speculate and not self.alias_logits:
             raise ValueError("FusedDecodeModel(speculate=True) needs alias_logits=True")
         self._epoch = 0
-        # One launch per token (cgq_step_*, csrc/decode_mk.cu) when the model fits it (fp16, every N a multiple of 32,
-        # K <= 13824); otherwise -- or with CGQ_ONE_LAUNCH=0 -- the PDL-chained 5 x layers + 2 launches.
-        self.one_launch = bool(int(os.environ.get("CGQ_ONE_LAUNCH", "1") or 1))
+        # one_launch=True (or CGQ_ONE_LAUNCH=1): the whole token as ONE persistent cooperative kernel (cgq_step_*,
+        # csrc/decode_mk.cu) when the model fits it (fp16, every N a multiple of 32, K <= 13824).  Correct and
+        # sanitizer-clean, but measured SLOWER than the PDL-chained 5 x layers + 2 launches (1.47 vs 1.19 ms per token on
+        # B200: ~2 us per grid barrier + ~2.5 us of serial prologue per phase, profiles/r02_step_program_timeline.txt),
+        # so it is opt-in.
+        self.one_launch = (bool(int(os.environ.get("CGQ_ONE_LAUNCH", "0") or 0)) if one_launch is None
+                           else bool(one_launch))
+        self.one_launch_refused = ""
         self._step_handle = None
         # last_logits_only=True: a prefill (several tokens) computes lm_head for the LAST position only and returns
         # logits [1, 1, V] -- all ChatGLMDecoder.generate reads is logits[0, -1] (decoder.py:85); at 2 048 tokens that

@@ -330,6 +330,92 @@ def prefetch_next_s4(b: Tensor, b_scale: Tensor) -> None:
     _lib.check(_lib.load().cgq_prefetch_next_w4(b.data_ptr(), b_scale.data_ptr(), b.shape[1], b.shape[0] * 2))
 
 
+EPI_NONE, EPI_SILU_PAIR = _lib.EPI_NONE, _lib.EPI_SILU_PAIR
+
+
+class StepProgram:
+    """A decode-step program (cgq_step_*, include/cgq.h): phases -- int4g32 linears with fused prologues / epilogues,
+    the RoPE + KV-append + attention of one query row, the embedding row -- executed strictly in order by ONE
+    persistent cooperative kernel (csrc/decode_mk.cu; one CTA per SM, weights streamed through a shared-memory
+    ring across phase boundaries, a grid barrier between phases).  `FusedDecodeModel` builds the whole token with
+    it; this class is the operator-level handle (tests, tools).  Every tensor must stay alive and in place while
+    the program exists (references are kept).  float16 only."""
+
+    def __init__(self, dtype: torch.dtype = torch.float16, state: Tensor = None):
+        if dtype != torch.float16:
+            raise TypeError("the one-launch step is built for float16 (the reference checkpoints' dtype)")
+        self.code = _DTYPE_CODE[dtype]
+        self.dtype = dtype
+        self.state = state            # [>= 1] int32: tokens in the KV cache before the step (attention phases)
+        self._ops: list = []
+        self._keep: list = [state]
+        self._handle = None
+
+    def linear(self, a: Tensor, b: Tensor, b_scale: Tensor, out: Tensor, bias: Tensor = None, resid: Tensor = None,
+               prologue: int = _lib.PRO_NONE, norm_weight: Tensor = None, eps: float = 0.0, epilogue: int = 0,
+               k: int = None) -> None:
+        """out[N] = (resid +) round(prologue(a) . dequant(b, b_scale)) (+ bias); EPI_SILU_PAIR stores
+        silu(out[:N/2]) * out[N/2:] into out[:N/2] instead.  `k` (default: from b) only documents intent."""
+        assert self._handle is None, "program already built"
+        K, N = b.shape[0] * 2, b.shape[1]
+        assert k is None or k == K
+        assert a.dtype == self.dtype and a.is_contiguous() and a.numel() >= (2 * K if prologue == _lib.PRO_SILU_GATE else K)
+        assert b.dtype == torch.uint8 and b.is_contiguous() and b_scale.is_contiguous() and b_scale.shape == (K // 32, N)
+        assert out.dtype == self.dtype and out.is_contiguous() and out.numel() >= (N // 2 if epilogue == EPI_SILU_PAIR else N)
+        self._ops.append(_lib.StepOp(kind=_lib.STEP_LINEAR, Wq=b.data_ptr(), scale=b_scale.data_ptr(), bias=_ptr(bias),
+                                     A=a.data_ptr(), C=out.data_ptr(), resid=_ptr(resid), norm_w=_ptr(norm_weight), N=N,
+                                     K=K, prologue=prologue, eps=float(eps), epilogue=epilogue))
+        self._keep += [a, b, b_scale, out, bias, resid, norm_weight]
+
+    def attention(self, qkv: Tensor, freqs: Tensor, k_cache: Tensor, v_cache: Tensor, out: Tensor, n_head: int,
+                  n_groups: int, d_head: int) -> None:
+        assert self._handle is None and self.state is not None, "attention phases need the `state` tensor"
+        max_len = k_cache.shape[0]
+        assert qkv.is_contiguous() and k_cache.is_contiguous() and v_cache.is_contiguous() and freqs.is_contiguous()
+        self._ops.append(_lib.StepOp(kind=_lib.STEP_ATTENTION, A=qkv.data_ptr(), C=out.data_ptr(), freqs=freqs.data_ptr(),
+                                     kcache=k_cache.data_ptr(), vcache=v_cache.data_ptr(), n_head=n_head,
+                                     n_groups=n_groups, d_head=d_head, max_len=max_len))
+        self._keep += [qkv, freqs, k_cache, v_cache, out]
+
+    def embed(self, ids: Tensor, weight: Tensor, weight_scale: Tensor, out: Tensor) -> None:
+        assert self._handle is None and ids.dtype == torch.int64
+        self._ops.append(_lib.StepOp(kind=_lib.STEP_EMBED, Wq=weight.data_ptr(), scale=weight_scale.data_ptr(),
+                                     C=out.data_ptr(), N=weight.shape[1], V=weight.shape[0] * 2, ids=ids.data_ptr()))
+        self._keep += [ids, weight, weight_scale, out]
+
+    def build(self) -> "StepProgram":
+        import ctypes
+
+        arr = (_lib.StepOp * len(self._ops))(*self._ops)
+        handle = ctypes.c_uint64(0)
+        dev = next(t for t in self._keep if t is not None).device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().cgq_step_create(arr, len(self._ops), self.code, _ptr(self.state), ctypes.byref(handle)))
+        self._handle, self._device = handle.value, dev
+        return self
+
+    def run(self) -> None:
+        if self._handle is None:
+            self.build()
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.load().cgq_step_run(self._handle, torch.cuda.current_stream().cuda_stream))
+
+    def status(self) -> tuple[int, int, bool]:
+        """(CTAs, ring stages per CTA, whether a grid barrier ever timed out) -- synchronises the device."""
+        import ctypes
+
+        c, st, f = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(_lib.load().cgq_step_status(self._handle, ctypes.byref(c), ctypes.byref(st), ctypes.byref(f)))
+        return c.value, st.value, bool(f.value)
+
+    def __del__(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().cgq_step_destroy(self._handle)
+            except Exception:  # noqa: BLE001
+                pass
+
+
 class DecodeProgram:
     """A chain of batch-1 int4g32 linears executed by ONE persistent launch (cgq_program_*, include/cgq.h).
 

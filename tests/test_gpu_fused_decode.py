@@ -147,12 +147,14 @@ def _duck_model(w, cfg):
                            freqs_cis_cache=to_torch(w["freqs"], "float16"))
 
 
-def test_fused_step_matches_reference_golden():
+@pytest.mark.parametrize("one_launch", [True, False])
+def test_fused_step_matches_reference_golden(one_launch):
     """Weights, prefill KV and greedy tokens of the REAL reference model (CPU fp16 fixture): the fused CUDA step
-    must reproduce its logits within the parity bar and pick the same tokens; also against the numpy oracle."""
+    -- as ONE persistent launch (cgq_step_*) and as the PDL chain of launches -- must reproduce its logits within
+    the parity bar and pick the same tokens; also against the numpy oracle."""
     w, cfg, fx = load_decode_golden()
     model = _duck_model(w, cfg)
-    fused = FusedDecodeModel(model, max_len=32)
+    fused = FusedDecodeModel(model, max_len=32, one_launch=one_launch)
     n0 = len(fx["prompt"])
     kv = tuple((to_torch(fx[f"prefill_k{i}"], "float16").reshape(1, n0, cfg["n_groups"], 1, cfg["d_head"]),
                 to_torch(fx[f"prefill_v{i}"], "float16").reshape(1, n0, cfg["n_groups"], 1, cfg["d_head"]))
@@ -171,6 +173,8 @@ def test_fused_step_matches_reference_golden():
             assert int(got.argmax()) == int(ref.argmax())
         want, okv = dec.decode_step(w, int(tok), okv, cfg, "float16")
         assert_parity(got, want, f"fused step {step} vs oracle")
+    assert fused.one_launch == one_launch, fused.one_launch_refused      # the requested path is the one that ran
+    assert fused.launches_per_step() == (1 if one_launch else 5 * cfg["n_layers"] + 2)
     n1 = n0 + len(fx["step_tokens"])
     for i, (k, v) in enumerate(fused._export_kv()):
         assert k.shape == (1, n1, cfg["n_groups"], 1, cfg["d_head"])
@@ -241,6 +245,7 @@ def test_fused_decode_matches_unmodified_reference_model(cfg_kwargs):
                 if (top2[0] - top2[1]).item() > 2e-2 * a.abs().max().item():
                     assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
                 tok = a.argmax().reshape(1, 1)
+        assert not fused.one_launch and fused.launches_per_step() == 5 * len(model.layers) + 2   # the default path
     finally:
         uninstall("chatglm_q")
 
@@ -395,3 +400,98 @@ def test_decode_program_bit_identical_to_per_linear_launches():
         assert torch.isfinite(got["logits"].float()).all()
         for k in ("x", "qkv", "u", "logits"):
             assert torch.equal(got[k], ref[k]), f"run {rep}: {k} differs from the launch-per-linear chain"
+
+
+# ------------------------------------------------------------------ one-launch step program (cgq_step_*)
+def _w4(seed, k, n, dtype="float16"):
+    _, bq, s = make_int4_case(seed, 1, k, n, "Q", dtype)
+    return bq, s
+
+
+@pytest.mark.parametrize("k,n", [(4096, 4608), (4096, 4096), (13696, 4096), (512, 768), (1056, 160), (4096, 65024)])
+def test_step_program_linear_prologues_vs_oracle(k, n):
+    """Single-phase step programs (one persistent launch each): RMSNorm + bias, plain + residual (in place),
+    SiLU-gate prologue, against the numpy oracle -- every real ChatGLM2-6B K / N plus ragged small shapes
+    (K not a multiple of the 512-k ring stage, one slice per CTA and fewer)."""
+    dt = "float16"
+    rng = np.random.default_rng(k + n)
+    bq, s = _w4(41, k, n)
+    x = orc.round_to(rng.standard_normal(k) * 2.0, dt)
+    nw = orc.round_to(1.0 + 0.2 * rng.standard_normal(k), dt)
+    bias = orc.round_to(rng.standard_normal(n) * 0.05, dt)
+    resid = orc.round_to(rng.standard_normal(n), dt)
+    W, S = u8(bq), to_torch(s, dt)
+    # (a) RMSNorm prologue + bias
+    out = torch.zeros(n, device=DEV, dtype=torch.float16)
+    prog = ops.StepProgram()
+    prog.linear(to_torch(x, dt), W, S, out, bias=to_torch(bias, dt), prologue=PRO_RMSNORM, norm_weight=to_torch(nw, dt), eps=1e-5)
+    prog.run()
+    ctas, stages, failed = prog.status()
+    assert not failed and ctas >= 1 and stages >= 2
+    want = orc.qmatmul_int4(dec.rmsnorm(x, nw, 1e-5, dt)[None], bq, s, bias, dt)[0]
+    assert_parity(from_torch(out), want, f"step program rmsnorm+bias K={k} N={n}")
+    first = out.clone()
+    prog.run()
+    torch.cuda.synchronize()
+    assert torch.equal(out, first), "two runs of the same program differ"
+    # (b) plain prologue, residual added in place
+    xr = to_torch(resid, dt)
+    prog = ops.StepProgram()
+    prog.linear(to_torch(x, dt), W, S, xr, resid=xr)
+    prog.run()
+    assert not prog.status()[2]
+    want = orc.round_to(resid + orc.qmatmul_int4(x[None], bq, s, None, dt)[0], dt)
+    assert_parity(from_torch(xr), want, f"step program plain+resid K={k} N={n}")
+    # (c) SiLU-gate prologue
+    u = orc.round_to(rng.standard_normal(2 * k) * 1.5, dt)
+    out = torch.zeros(n, device=DEV, dtype=torch.float16)
+    prog = ops.StepProgram()
+    prog.linear(to_torch(u, dt), W, S, out, prologue=PRO_SILU_GATE)
+    prog.run()
+    assert not prog.status()[2]
+    want = orc.qmatmul_int4(dec.silu_gate(u, dt)[None], bq, s, None, dt)[0]
+    assert_parity(from_torch(out), want, f"step program silu-gate K={k} N={n}")
+
+
+@pytest.mark.parametrize("k,inner", [(4096, 13696), (256, 384), (512, 1024)])
+def test_step_program_swiglu_pair_epilogue_then_w_out(k, inner):
+    """w_in with CGQ_EPI_SILU_PAIR followed by w_out (+ residual) in ONE program, two dependent phases with a grid
+    barrier between them: u = silu(h) * gate must be BIT-equal to the oracle's roundings of this kernel's own w_in
+    output, and the block's result within the bar of the oracle."""
+    dt = "float16"
+    rng = np.random.default_rng(inner)
+    w_in, s_in = _w4(51, k, 2 * inner)
+    w_out, s_out = _w4(52, inner, k)
+    x = orc.round_to(rng.standard_normal(k), dt)
+    resid = orc.round_to(rng.standard_normal(k), dt)
+    raw = torch.zeros(2 * inner, device=DEV, dtype=torch.float16)
+    plain = ops.StepProgram()
+    plain.linear(to_torch(x, dt), u8(w_in), to_torch(s_in, dt), raw)
+    plain.run()
+    u = torch.zeros(2 * inner, device=DEV, dtype=torch.float16)
+    y = to_torch(resid, dt)
+    prog = ops.StepProgram()
+    prog.linear(to_torch(x, dt), u8(w_in), to_torch(s_in, dt), u, epilogue=ops.EPI_SILU_PAIR)
+    prog.linear(u, u8(w_out), to_torch(s_out, dt), y, resid=y, k=inner)
+    prog.run()
+    assert not prog.status()[2]
+    got_u = from_torch(u[:inner])
+    want_u = dec.silu_gate(from_torch(raw), dt)
+    diff = np.abs(got_u - want_u)
+    # device exp / divide vs numpy: the value is rounded to fp16 twice, a last-fp32-bit difference shows rarely
+    assert (diff <= np.abs(want_u) * 2.0 ** -9 + 1e-7).all() and (diff == 0).mean() > 0.97, (diff.max(), (diff == 0).mean())
+    h = orc.qmatmul_int4(x[None], w_in, s_in, None, dt)[0]
+    want = orc.round_to(resid + orc.qmatmul_int4(dec.silu_gate(h, dt)[None], w_out, s_out, None, dt)[0], dt)
+    assert_parity(from_torch(y), want, f"step program swiglu block K={k} inner={inner}")
+
+
+def test_step_program_rejects_what_it_cannot_take():
+    x = torch.zeros(64, device=DEV, dtype=torch.float16)
+    w = torch.zeros((32, 48), device=DEV, dtype=torch.uint8)          # N = 48 is not a multiple of the 32-column slice
+    s = torch.zeros((2, 48), device=DEV, dtype=torch.float16)
+    prog = ops.StepProgram()
+    prog.linear(x, w, s, torch.zeros(48, device=DEV, dtype=torch.float16))
+    with pytest.raises(Exception, match="multiple of 32"):
+        prog.build()
+    with pytest.raises(TypeError):
+        ops.StepProgram(torch.bfloat16)

@@ -315,8 +315,9 @@ int main(int argc, char** argv) {
              memcmp(got.data(), got2.data(), VOCAB * 2) == 0 ? "yes" : "NO");
       if (failed) return 2;
       if (getenv("CGQ_STEP_TRACE")) {
+        // in-kernel timeline (cgq_debug_trace): 8 stamps per (op, CTA), see decode_mk.cu
         uint64_t* tr;
-        const size_t words = ops.size() * (size_t)ctas;
+        const size_t words = ops.size() * (size_t)ctas * 8;
         CK(cudaMalloc(&tr, words * 8));
         CK(cudaMemsetAsync(tr, 0, words * 8, st));
         CK(cudaMemcpy(state, st0, 8, cudaMemcpyHostToDevice));
@@ -326,14 +327,23 @@ int main(int argc, char** argv) {
         std::vector<uint64_t> hh(words);
         CK(cudaMemcpy(hh.data(), tr, words * 8, cudaMemcpyDeviceToHost));
         const char* kinds[3] = {"linear", "attn", "embed"};
+        const char* nm[7] = {"barrier", "staged", "stage1", "loop_w0", "loop_w15", "stored", "arrive"};
         for (size_t op = 6; op <= 11 && op < ops.size(); ++op) {
-          uint64_t mn = ~0ull, mx = 0, pmn = ~0ull;
-          for (int c = 0; c < ctas; ++c) {
-            mn = std::min(mn, hh[op * ctas + c]); mx = std::max(mx, hh[op * ctas + c]);
-            pmn = std::min(pmn, hh[(op - 1) * ctas + c]);
+          uint64_t t0 = ~0ull;
+          for (int c = 0; c < ctas; ++c)
+            if (hh[(op * ctas + c) * 8]) t0 = std::min(t0, hh[(op * ctas + c) * 8]);
+          printf("  op %zu (%s N=%d K=%d), us after the first CTA left the barrier [min avg max]:", op, kinds[ops[op].kind],
+                 ops[op].N, ops[op].K);
+          for (int sl = 0; sl < 7; ++sl) {
+            uint64_t mn = ~0ull, mx = 0; double sum = 0; int cnt = 0;
+            for (int c = 0; c < ctas; ++c) {
+              const uint64_t v = hh[(op * ctas + c) * 8 + sl];
+              if (!v) continue;
+              mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)(v - t0); ++cnt;
+            }
+            if (cnt) printf("  %s %.2f %.2f %.2f", nm[sl], (mn - t0) / 1e3, sum / cnt / 1e3, (mx - t0) / 1e3);
           }
-          printf("  barrier before op %zu (%s N=%d K=%d): previous phase took %.2f us, exit spread %.2f us\n", op,
-                 kinds[ops[op].kind], ops[op].N, ops[op].K, (mn - pmn) / 1e3, (mx - mn) / 1e3);
+          printf("\n");
         }
       }
       cudaGraph_t g;
