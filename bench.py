@@ -218,6 +218,94 @@ class TokenStep:
         return logits
 
 
+class TPTokenStep:
+    """N > 1: the same 113 dequant-matmuls, tensor-parallel (chatglm_q_b200/tp.py): every rank generates the SAME full
+    weights (same seed) and cuts its shards from them -- column slices of qkv / w_in / lm_head, k-row slices of
+    o_proj / w_out.  The row-parallel linears exchange their fp32 partial sums INSIDE the decode kernel's epilogue
+    over NVLink peer memory (cgq_tp_next, include/cgq.h): no NCCL call on the token path.  lm_head stores its
+    vocabulary slice into every rank's logits row, one cross-GPU barrier kernel ends the step.  The full weights stay
+    on the rank for the parity gate (TP logits vs the unsharded chain on the same inputs)."""
+
+    def __init__(self, torch, device, world: int, rank: int):
+        from chatglm_q_b200 import ops, tp
+
+        self.torch, self.ops, self.world, self.rank = torch, ops, world, rank
+        self.plan, block, head = token_linears(world, rank)
+        gen = torch.Generator(device=device).manual_seed(1234)          # identical on every rank
+        full_block = [("qkv_proj", H, QKV_N, True), ("o_proj", H, H, False), ("w_in", H, 2 * INNER, False),
+                      ("w_out", INNER, H, False)]
+        shards = (self.plan.qkv, self.plan.o, self.plan.w_in, self.plan.w_out)
+        self.full, self.layers = [], []
+        for _ in range(LAYERS):
+            fl, sl = [], []
+            for (name, k, n, bias), sh in zip(full_block, shards):
+                w, s, b = make_w4(torch, k, n, bias, device, gen)
+                fl.append((w, s, b))
+                sl.append(tp.shard_w4(w, s, b, sh, rank=0))
+            self.full.append(fl)
+            self.layers.append(sl)
+        self.full_head = make_w4(torch, H, VOCAB, False, device, gen)
+        self.head = tp.shard_w4(*self.full_head, self.plan.lm_head, rank=0)
+        self.x0 = torch.randn((1, H), device=device, generator=torch.Generator(device=device).manual_seed(99)).half()
+        self.bytes = LAYERS * sum(w4_bytes(1, k, n, b) for _, k, n, b in block) + w4_bytes(1, head[1], head[2], False)
+        self.launches = LAYERS * 4 + 1
+        self.kq, self.ki = block[1][1], block[3][1]          # o_proj / w_out K on this rank
+        z = lambda n: torch.zeros(n, device=device, dtype=torch.float16)  # noqa: E731
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)     # [2] = token counter (exchange epochs)
+        self.x, self.qkv, self.o, self.hin = z(H), z(block[0][2]), z(H), z(block[2][2])
+        self.ex = tp.TpExchange(H, VOCAB, self.state[2:], None)
+        self.logits = self.ex.logits
+        self.v0 = self.plan.lm_head.cols[0][0]
+        self.one = torch.ones(1, dtype=torch.int32, device=device)
+
+    def run(self):
+        ops, ex = self.ops, self.ex
+        self.state[2:3].add_(self.one)                          # what cgq_decode_begin_w4 does in the fused step
+        self.x.copy_(self.x0[0])
+        idx = 0
+        for (wq, sq, bq), (wo, so, _), (wi, si, _), (wu, su, _) in self.layers:
+            ops.gemv_fused_s4(self.x, wq, sq, bias=bq, out=self.qkv)
+            ex.next_reduce(idx)
+            ops.gemv_fused_s4(self.qkv[:self.kq], wo, so, out=self.o)          # stand-in for attention out: this rank's q columns
+            ops.gemv_fused_s4(self.o, wi, si, out=self.hin)
+            ex.next_reduce(idx + 1)
+            ops.gemv_fused_s4(self.hin[:self.ki], wu, su, out=self.x)          # stand-in for silu(h)*gate: this rank's h columns
+            idx += 2
+        ex.next_broadcast(self.v0)
+        ops.gemv_fused_s4(self.x, *self.head[:2], out=self.logits)
+        ex.barrier(self.torch.cuda.current_stream().cuda_stream)
+        return self.logits
+
+    def run_unsharded(self):
+        """The same chain on the full weights with the single-GPU launches: the parity gate's reference."""
+        ops = self.ops
+        x = self.x0
+        for (wq, sq, bq), (wo, so, _), (wi, si, _), (wu, su, _) in self.full:
+            qkv = ops.dynamic_quant_matmul_s4(x, wq, sq, bias=bq)
+            o = ops.dynamic_quant_matmul_s4(qkv[:, :H], wo, so)
+            hin = ops.dynamic_quant_matmul_s4(o, wi, si)
+            x = ops.dynamic_quant_matmul_s4(hin[:, :INNER], wu, su)
+        return ops.dynamic_quant_matmul_s4(x, *self.full_head[:2])[0]
+
+    def parity_gate(self, dist):
+        """TP logits against the unsharded chain on every rank (bar: |d| <= 2e-2 |ref| + 2e-2 rms -- two
+        implementations of a 28-block chain with different summation orders), identical rows on all ranks, no lost
+        peer word."""
+        torch = self.torch
+        ref = self.run_unsharded().float()
+        got = self.run().float().clone()
+        torch.cuda.synchronize()
+        rms = ref.pow(2).mean().sqrt()
+        ratio = ((got - ref).abs() / (2e-2 * ref.abs() + 2e-2 * rms)).max()
+        t = torch.stack([ratio, got.double().sum().float(), -got.double().sum().float()])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = self.ex.error()
+        return {"worst_ratio": round(float(t[0]), 4), "bar": "2e-2 * (|ref| + rms(ref)), 28-block chain, max over ranks",
+                "ok": bool(t[0] <= 1.0) and err == 0 and bool(torch.isfinite(got).all()),
+                "rows_identical_on_all_ranks": bool(t[1] == -t[2]), "lost_peer_words": err,
+                "reference": "unsharded chain of the same weights through the single-GPU launches, on every rank"}
+
+
 # ----------------------------------------------------------------------------- microbench (configs[1])
 def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392), k=4096, iters=10):
     """BASELINE.json configs[1]: (seq x 4096) x (4096 x N) int4g32 dequant-matmul.  Per shape a CUDA graph
@@ -445,7 +533,7 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
         for i in range(reps + 5):
             if i == 5:
                 e0.record()
-            fused_model.state.copy_(st, non_blocking=True)
+            fused_model.state[:2].copy_(st, non_blocking=True)
             fused_model.graph.replay()
         e1.record()
         torch.cuda.synchronize()
@@ -601,10 +689,13 @@ def run_own_arm(args):
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
 
-    step = TokenStep(torch, device, world, rank)
+    step = TokenStep(torch, device, world, rank) if world == 1 else TPTokenStep(torch, device, world, rank)
     stream = torch.cuda.Stream(device=device)
+    tp_parity = None
     with torch.cuda.stream(stream), torch.no_grad():
-        for _ in range(2):          # tensor-map cache, workspace, NCCL channels
+        if world > 1:               # parity gate BEFORE anything is timed
+            tp_parity = step.parity_gate(dist)
+        for _ in range(2):          # tensor-map cache, workspace
             step.run()
         stream.synchronize()
         graph = None
@@ -644,6 +735,8 @@ def run_own_arm(args):
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
     assert torch.isfinite(step.logits.float()).all(), "non-finite logits from the token step"
+    if world > 1:
+        assert step.ex.error() == 0, f"a peer's exchange word never arrived (epoch {step.ex.error()})"
 
     total_bytes = step.bytes   # this rank's algorithmic bytes per step (all ranks stream concurrently)
     achieved = total_bytes / (ms_per_step * 1e-3) / 1e9
@@ -655,7 +748,8 @@ def run_own_arm(args):
                 "algorithmic_bytes_per_launch": round(total_bytes / step.launches),
                 "algorithmic_bytes_per_step": total_bytes, "launches_per_step": step.launches,
                 "avg_launch_us": round(ms_per_step * 1e3 / step.launches, 3),
-                "note": "per rank; includes the inter-kernel gaps of the graph-replayed step (and NCCL at N>1)"}
+                "note": "per rank; includes the inter-kernel gaps of the graph-replayed step (at N>1: and the in-kernel "
+                        "NVLink exchange of the row-parallel linears + the end-of-step barrier kernel)"}
     del graph, step
     torch.cuda.empty_cache()
 
@@ -667,6 +761,7 @@ def run_own_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": bench_config(world),
             "launch": "no CUDA graph" if args.no_graph else "CUDA graph replay of the C-ABI launches",
+            "tp_parity": tp_parity,
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(roofline["launches_per_step"] * args.steps),
         }
     if world == 1:
@@ -697,11 +792,11 @@ def run_own_arm(args):
         def bail():
             if rank == 0:
                 line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": H * 2, "d2h_bytes_per_step": 8,
-                               "note": "TP e2e leg did not finish within 120 s and was abandoned"}
+                               "note": "TP e2e leg did not finish within 420 s and was abandoned"}
                 print(json.dumps(line), flush=True)
             os._exit(0)
 
-        dog = threading.Timer(120.0, bail)
+        dog = threading.Timer(420.0, bail)
         dog.daemon = True
         dog.start()
         line_e2e = tp_e2e(torch, device, world, rank, args)
@@ -722,30 +817,108 @@ def run_own_arm(args):
 
 
 def tp_e2e(torch, device, world, rank, args):
-    """N>1: the TP token step with the hidden state copied from pinned host memory and the gathered
-    logits' argmax read back, every step (no graph across the host round trip)."""
+    """N>1 end to end: the UNMODIFIED reference `ChatGLMDecoder.generate` on EVERY rank, driving
+    chatglm_q_b200.TPFusedDecodeModel (the fused decode step sharded over the ranks, in-kernel NVLink exchange); every
+    rank samples from the identical all-gathered logits with the same seed, so no token is ever broadcast.  Each step
+    copies the token id host->device and reads the sampled token back.  Before timing: greedy parity gate of the TP
+    step against the single-GPU fused step on the same model (logits within the 2e-2 chain bar, same tokens)."""
     import torch.distributed as dist
 
-    step = TokenStep(torch, device, world, rank)
-    host_x = torch.randn(1, H, generator=torch.Generator().manual_seed(7)).half().pin_memory()
-    stream = torch.cuda.Stream(device=device)      # (same kind of stream as the timed region, not the legacy one)
-    with torch.cuda.stream(stream), torch.no_grad():
-        for _ in range(3):
-            step.x.copy_(host_x, non_blocking=True)
-            int(step.run().argmax().item())
+    if import_reference() is None:
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "baseline/_ref missing: reference decoder not importable"}
+    from chatglm_q.decoder import ChatGLMDecoder
+    import chatglm_q.decoder as decmod
+    from chatglm_q_b200.fused_decode import FusedDecodeModel
+    from chatglm_q_b200.install import install, uninstall
+    from chatglm_q_b200.tp_decode import TPFusedDecodeModel
+
+    prompt_len, gen_tokens = 32, args.gen_tokens
+    install("chatglm_q", sampler=True)
+    try:
+        cfg, model = build_ref_int4_model(torch, device)           # same seed on every rank: identical full models
+        max_len = prompt_len + gen_tokens + 32
+        tpm = TPFusedDecodeModel(model, max_len=max_len)
+        one = FusedDecodeModel(model, max_len=max_len)
+        # ---- parity gate: prefill + 6 greedy steps through both wrappers
+        prompt = torch.tensor([StubTokenizer(prompt_len).encode("x")], device=device)
+        worst, same_tok = 0.0, True
+        with torch.no_grad():
+            _, lg1, h1 = one(input_ids=prompt, past_key_values=None)
+            _, lgt, ht = tpm(input_ids=prompt, past_key_values=None)
+            tok = lg1[0, -1].argmax().reshape(1, 1)
+            for _ in range(6):
+                _, lg1, h1 = one(input_ids=tok, past_key_values=h1)
+                _, lgt, ht = tpm(input_ids=tok, past_key_values=ht)
+                a, b = lg1[0, -1].float(), lgt[0, -1].float()
+                rms = a.pow(2).mean().sqrt()
+                worst = max(worst, float(((a - b).abs() / (2e-2 * a.abs() + 2e-2 * rms)).max()))
+                top2 = a.topk(2).values
+                if float(top2[0] - top2[1]) > 2e-2 * float(a.abs().max()):
+                    same_tok = same_tok and int(a.argmax()) == int(b.argmax())
+                tok = a.argmax().reshape(1, 1)
+        t = torch.tensor([worst, 0.0 if same_tok else 1.0], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gate = {"worst_ratio": round(float(t[0]), 4), "same_greedy_tokens": bool(t[1] == 0), "lost_peer_words": tpm.ex.error(),
+                "ok": bool(t[0] <= 1.0 and t[1] == 0) and tpm.ex.error() == 0,
+                "how": "prefill + 6 greedy steps: TPFusedDecodeModel vs the single-GPU FusedDecodeModel on the same model, "
+                       "|d| <= 2e-2 |ref| + 2e-2 rms, every rank"}
+        del one
+        # ---- timed generation, tok/s exactly as the reference's `gen` figure
+        real_perf = time.perf_counter
+        times = []
+
+        class _Clock:
+            @staticmethod
+            def perf_counter():
+                tt = real_perf()
+                times.append(tt)
+                return tt
+
+            def __getattr__(self, k):
+                return getattr(time, k)
+
+        dec = ChatGLMDecoder(cfg, tpm, StubTokenizer(prompt_len), device=device, time_log=False)
+        torch.manual_seed(0)
+        for _ in dec.generate("warm-up", max_generated_tokens=8):
+            pass
         dist.barrier()
         torch.cuda.synchronize()
-        n = max(5, min(args.steps, 50))
-        t0 = time.perf_counter()
-        for _ in range(n):
-            step.x.copy_(host_x, non_blocking=True)
-            int(step.run().argmax().item())
+        decmod.time = _Clock()
+        try:
+            for _ in dec.generate("bench", max_generated_tokens=gen_tokens):
+                pass
+        finally:
+            decmod.time = time
+        steps = [b - a for a, b in zip(times[0::2], times[1::2])]
+        rest = steps[1:]
+        tt = torch.tensor([sum(rest)], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # device time of the TP fused step alone (graph replays, KV window rewound)
+        ctx = prompt_len + gen_tokens // 2
+        st = torch.tensor([ctx, ctx], dtype=torch.int32, device=device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        dist.barrier()
+        for i in range(reps + 5):
+            if i == 5:
+                e0.record()
+            tpm.state[:2].copy_(st, non_blocking=True)
+            tpm.graph.replay()
+        e1.record()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"value": round(n / float(t.item()), 2), "unit": UNIT, "h2d_bytes_per_step": H * 2, "d2h_bytes_per_step": 8,
-            "how": "TP token step through chatglm_q_b200.ops from a pinned host activation, argmax read back each step"}
+        dev = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=device)
+        dist.all_reduce(dev, op=dist.ReduceOp.MAX)
+        return {"value": round(len(rest) / float(tt.item()), 2), "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+                "tokens": len(steps), "parity_gate": gate, "fused_step_device_us": round(float(dev.item()), 1),
+                "fused_step_launches": tpm.launches_per_step(), "lost_peer_words": tpm.ex.error(),
+                "how": f"reference ChatGLMDecoder.generate (unmodified) on every rank driving TPFusedDecodeModel (tp{world}: "
+                       f"column-parallel qkv / w_in / lm_head, row-parallel o_proj / w_out with the partial sums exchanged "
+                       f"inside the decode kernel over NVLink peer memory, logits all-gathered by peer stores + one barrier "
+                       f"kernel); one CUDA-graph replay per token; same seed on every rank, no token broadcast; "
+                       f"max over ranks of the summed step wall time"}
+    finally:
+        uninstall("chatglm_q")
 
 
 def main():

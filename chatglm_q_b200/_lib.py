@@ -34,6 +34,12 @@ SYMBOLS = {
     "cgq_step_run": (c_int, [ctypes.c_uint64, c_void_p]),
     "cgq_step_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p, c_void_p]),
     "cgq_step_destroy": (c_int, [ctypes.c_uint64]),
+    "cgq_tp_next": (c_int, [c_void_p, ctypes.c_uint32]),
+    "cgq_tp_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cgq_ipc_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "cgq_ipc_open": (c_int, [c_void_p, c_void_p]),
+    "cgq_ipc_close": (c_int, [c_void_p]),
+    "cgq_ipc_free": (c_int, [c_void_p]),
     "cgq_prefetch_next_w4": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "cgq_decode_begin_w4": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_void_p, c_void_p]),
@@ -73,6 +79,12 @@ class StepOp(ctypes.Structure):
                 ("prologue", c_int), ("eps", c_float), ("epilogue", c_int), ("freqs", c_void_p), ("kcache", c_void_p), ("vcache", c_void_p),
                 ("n_head", c_int), ("n_groups", c_int), ("d_head", c_int), ("max_len", c_int), ("ids", c_void_p),
                 ("V", c_int)]
+
+
+class TpCtx(ctypes.Structure):
+    """`cgq_tp_ctx` of include/cgq.h (tensor-parallel exchange of the fused decode step)."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("max_n", c_int), ("out_offset", c_int), ("recv", c_void_p * 8),
+                ("step", c_void_p), ("err", c_void_p), ("out", c_void_p * 8)]
 
 
 class CgqError(RuntimeError):

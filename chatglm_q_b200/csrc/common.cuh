@@ -99,6 +99,7 @@ int launch_w4_simple(const GemmArgs& a);
 int launch_w4_gemv_fused(const GemmArgs& a, const GemvFused& fu);
 void set_next_w4_hint(const void* w, const void* s, int N, int K);
 void set_w4_handover(const unsigned* wait_ctr, unsigned wait_count, unsigned* signal_ctr);
+void set_w4_tp(const cgq_tp_ctx& ctx, unsigned idx);
 int w4_gemv_tiles(int N);
 int launch_w8_simple(const GemmArgs& a);
 int launch_w4_gemv(const GemmArgs& a, bool exact);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256)
     const int cur = state[0];
     state[1] = cur;
     state[0] = cur + 1;
+    state[2] = state[2] + 1;     // token counter (epoch source of the tensor-parallel exchanges)
     __threadfence();
   }
   __syncthreads();

@@ -36,6 +36,7 @@
 //     (the producer answers a release with a TMA write into the same slot; a refill that hit L2 used to
 //     land before the stage's scale loads in ~10 % of the M = 8 launches).
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -92,6 +93,15 @@ struct Params {
   // root-cause experiment only (CGQ_HACK_PLAIN_RELEASE=1, M > 1 kernels): release ring slots with a plain
   // mbarrier.arrive, i.e. the pre-fix protocol that lets the arrive overtake outstanding ld.shared
   int plain_release;
+  // tensor parallelism (cgq_tp_next, M == 1 fused launches only; no reference counterpart -- SURVEY §8e):
+  //  * tp.recv[0] != null: ROW-parallel linear.  The fp32 partial sum of every output column is exchanged with the
+  //    peer ranks in the epilogue (8-byte {value, epoch} words stored straight into every rank's receive buffer over
+  //    NVLink, NCCL-LL style: no fence, no flag, no collective launch) and summed in rank order -- every rank ends
+  //    up with the bit-identical row;
+  //  * tp.out[0] != null: COLUMN-parallel linear whose output every rank needs whole (lm_head): the rounded values
+  //    are stored into every rank's output buffer at this rank's column offset.
+  cgq_tp_ctx tp;
+  unsigned tp_idx;
 };
 constexpr int kPfPiece = 16384;
 
@@ -181,6 +191,49 @@ __device__ __forceinline__ void signal_tile(const Params& p) {
   }
 }
 
+// One-shot all-reduce of a row-parallel linear's partial sums.  Word (slot, src rank, column) of a
+// rank's receive buffer holds {fp32 partial, epoch}; epoch = step_no * 128 + exchange index + 1 is unique per
+// (token, linear), the two slots alternate between consecutive exchanges.  A rank can only reach exchange i + 2
+// after every peer has published exchange i + 1, i.e. after every peer has finished reading exchange i: two slots
+// are enough.  The spin is bounded: a lost peer sets a sticky error word instead of hanging the device.
+__device__ __forceinline__ float tp_allreduce(const cgq_tp_ctx& tp, unsigned idx, int step_no, float acc, int n) {
+  const unsigned epoch = (static_cast<unsigned>(step_no) << 7) + idx + 1u;
+  const size_t slot_words = static_cast<size_t>(tp.world) * tp.max_n;
+  const size_t base = (idx & 1u) * slot_words;
+  const size_t mine = base + static_cast<size_t>(tp.rank) * tp.max_n + n;
+  for (int r = 0; r < tp.world; ++r) {
+    uint2* dst = static_cast<uint2*>(tp.recv[r]) + mine;
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(acc)), "r"(epoch) : "memory");
+  }
+  float sum = 0.f;
+  const uint2* own = static_cast<const uint2*>(tp.recv[tp.rank]) + base + n;
+  for (int r = 0; r < tp.world; ++r) {
+    const uint2* src = own + static_cast<size_t>(r) * tp.max_n;
+    unsigned v, e, spins = 0;
+    for (;;) {
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+      if (e == epoch) break;
+      if (++spins > (1u << 26)) {
+        if (tp.err != nullptr) *tp.err = epoch;
+        break;
+      }
+    }
+    sum += __uint_as_float(v);
+  }
+  return sum;
+}
+// final value of output column n: (all-reduce) -> round -> bias -> residual -> store (to every rank for tp.out)
+template <typename T>
+__device__ __forceinline__ void store_column(const Params& p, float acc, int n, int step_no) {
+  if (p.tp.world > 1 && p.tp.recv[0] != nullptr) acc = tp_allreduce(p.tp, p.tp_idx, step_no, acc, n);
+  const T val = add_resid<T>(epilogue<T>(acc, static_cast<const T*>(p.bias), n), static_cast<const T*>(p.resid), n);
+  if (p.tp.world > 1 && p.tp.out[0] != nullptr) {
+    for (int r = 0; r < p.tp.world; ++r) static_cast<T*>(p.tp.out[r])[p.tp.out_offset + n] = val;
+  } else {
+    static_cast<T*>(p.C)[n] = val;
+  }
+}
+
 template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
 __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     w4_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmS,
@@ -208,6 +261,10 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   const int u0 = p.SPT * z / Z, u1 = p.SPT * (z + 1) / Z;      // this CTA's k-stages of the tile
   const int n_units = u1 - u0;
   const T* A = static_cast<const T*>(p.A);
+  // token counter of the step (published by cgq_decode_begin_w4 before it releases its dependents, like state[1])
+  int step_no = 0;
+  if (kM1 && p.tp.world > 1 && p.tp.step != nullptr)
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(step_no) : "l"(p.tp.step));
 
   // ---- prologue: barriers
   if (threadIdx.x == CW * 32) {
@@ -588,13 +645,15 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     if (Z == 1) {
       const int n = tile * BN + t;
       if (n < p.N) {
-        T* Cp = static_cast<T*>(p.C);
-        const T* bias = static_cast<const T*>(p.bias);
+        if constexpr (kM1) {
+          store_column<T>(p, v[0], n, step_no);
+        } else {
+          T* Cp = static_cast<T*>(p.C);
+          const T* bias = static_cast<const T*>(p.bias);
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < p.M)
-            Cp[m * p.ldc + n] = add_resid<T>(epilogue<T>(v[m], bias, n),
-                                             kM1 ? static_cast<const T*>(p.resid) : nullptr, n);
+          for (int m = 0; m < MR; ++m)
+            if (m < p.M) Cp[m * p.ldc + n] = epilogue<T>(v[m], bias, n);
+        }
       }
       signal_tile<kHand>(p);
     } else {
@@ -621,8 +680,10 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
           if (m < p.M) {
             float acc = 0.f;
             for (int zz = 0; zz < Z; ++zz) acc += xred[(zz * MR + m) * BN + t];
-            Cp[m * p.ldc + n] = add_resid<T>(epilogue<T>(acc, bias, n),
-                                             kM1 ? static_cast<const T*>(p.resid) : nullptr, n);
+            if constexpr (kM1)
+              store_column<T>(p, acc, n, step_no);
+            else
+              Cp[m * p.ldc + n] = epilogue<T>(acc, bias, n);
           }
         }
       }
@@ -670,6 +731,12 @@ struct Handover {
   unsigned* signal_ctr;
 };
 thread_local Handover g_hand = {nullptr, 0, nullptr};
+struct TpHint {
+  cgq_tp_ctx ctx;
+  unsigned idx;
+  bool set;
+};
+thread_local TpHint g_tp = {{}, 0, false};
 
 template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
@@ -786,6 +853,16 @@ int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
   prm.band_units = per_cta;
   static const int plain_release = env_int("CGQ_HACK_PLAIN_RELEASE", 0, 0, 1);
   prm.plain_release = plain_release;
+  // one-shot tensor-parallel hint (cgq_tp_next); only the fused M == 1 launches take it
+  memset(&prm.tp, 0, sizeof(prm.tp));
+  prm.tp_idx = 0;
+  if (g_tp.set) {
+    if (fu != nullptr && a.M == 1) {
+      prm.tp = g_tp.ctx;
+      prm.tp_idx = g_tp.idx;
+    }
+    g_tp.set = false;
+  }
   // one-shot hand-over hint (cgq_handover_next); only the fused M == 1 launches take it
   const Handover hand = g_hand;
   g_hand = Handover{nullptr, 0, nullptr};
@@ -861,6 +938,12 @@ int launch_w4_gemv(const GemmArgs& a, bool exact) {
 
 void set_next_w4_hint(const void* w, const void* s, int N, int K) {
   g_next = NextHint{w, s, N, K};
+}
+
+void set_w4_tp(const cgq_tp_ctx& ctx, unsigned idx) {
+  g_tp.ctx = ctx;
+  g_tp.idx = idx;
+  g_tp.set = true;
 }
 
 void set_w4_handover(const unsigned* wait_ctr, unsigned wait_count, unsigned* signal_ctr) {

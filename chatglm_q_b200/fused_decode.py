@@ -134,7 +134,7 @@ class FusedDecodeModel:
         H, DH, NH, NG = cfg.hidden_size, cfg.head_hidden_size, cfg.num_attention_heads, cfg.num_multi_query_groups
         z = lambda *shape, dtype=dt: torch.zeros(shape, device=device, dtype=dtype)  # noqa: E731
         self.ids = z(1, 1, dtype=torch.long)
-        self.state = z(2, dtype=torch.int32)
+        self.state = z(4, dtype=torch.int32)      # [0] cached tokens, [1] this step's value, [2] token counter
         self.x = z(H)
         self.qkv = z(DH * (NH + 2 * NG))
         self.ao = z(DH * NH)
@@ -283,12 +283,13 @@ class FusedDecodeModel:
         with torch.cuda.stream(side), torch.cuda.device(dev):
             self._launch_step()                       # warm-up: tensor maps, function attributes
             side.synchronize()
-            self.state.copy_(state0)                  # the warm-up step consumed a position; take it back
+            self.state[:2].copy_(state0[:2])          # the warm-up step consumed a position; take it back (the token
+                                                      # counter state[2] keeps counting: exchange epochs never repeat)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
                 self._launch_step()
         torch.cuda.current_stream(dev).wait_stream(side)
-        self.state.copy_(state0)
+        self.state[:2].copy_(state0[:2])
 
     # ---------------------------------------------------------------- model(...) as the decoder calls it
     @torch.no_grad()
@@ -370,7 +371,7 @@ class FusedDecodeModel:
         if self._spec or rewind:
             self._spec = False
             if rewind:
-                self.state.copy_(torch.tensor([self.n_valid, self.n_valid], dtype=torch.int32), non_blocking=False)
+                self.state[:2].copy_(torch.tensor([self.n_valid, self.n_valid], dtype=torch.int32), non_blocking=False)
 
     def _can_speculate(self, logits: Tensor) -> bool:
         return (self.speculate and self._ready and self.graph is not None and self._host_ids
@@ -426,7 +427,7 @@ class FusedDecodeModel:
         for (ks, vs), (k, v) in zip(self.kv, kv):
             ks[:, :n].copy_(k)
             vs[:, :n].copy_(v)
-        self.state.copy_(torch.tensor([n, n], dtype=torch.int32), non_blocking=False)
+        self.state[:2].copy_(torch.tensor([n, n], dtype=torch.int32), non_blocking=False)
 
     def _export_kv(self):
         if self._eager_kv is not None:      # the cache lives outside the static buffers (batch > 1, window exhausted)

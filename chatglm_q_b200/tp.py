@@ -182,3 +182,121 @@ def gather_columns(part: Tensor, sh: Shard, n_full: int, group=None) -> Tensor:
     parts = [torch.empty_like(part) for _ in range(world)]
     dist.all_gather(parts, part.contiguous(), group=group)
     return torch.cat(parts, dim=-1)
+
+
+# ---------------------------------------------------------------------- peer-visible device memory (NVLink P2P)
+class PeerMemory:
+    """`nbytes` of zeroed device memory on every rank of `group`, each rank's block mapped into every other rank's
+    address space (cgq_ipc_*: cudaMalloc + legacy CUDA IPC handles, exchanged here over torch.distributed).
+    `ptrs[r]` is rank r's block as seen from THIS process (ptrs[rank] = the local allocation): the decode kernels
+    store their partial sums / logits straight into peers' blocks over NVLink (include/cgq.h, cgq_tp_ctx).
+    torch is plumbing only: the handle exchange and a tensor view of the local block."""
+
+    def __init__(self, nbytes: int, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        lib = _lib.load()
+        self._lib, self.group = lib, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = int(nbytes)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        local = ctypes.c_void_p(0)
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.cgq_ipc_alloc(self.nbytes, ctypes.byref(local), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(local.value)
+                continue
+            p = ctypes.c_void_p(0)
+            _lib.check(lib.cgq_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        self._local = local.value
+        dist.barrier(group=group)          # every rank has mapped every block before anyone stores into one
+
+    def tensor(self, dtype: torch.dtype, numel: int, byte_offset: int = 0) -> Tensor:
+        """A torch view of the LOCAL block (through __cuda_array_interface__; the memory stays owned by this object)."""
+        typestr = {torch.float16: "<f2", torch.int32: "<i4", torch.uint8: "|u1", torch.float32: "<f4",
+                   torch.int64: "<i8"}[dtype]
+        assert byte_offset + numel * torch.empty((), dtype=dtype).element_size() <= self.nbytes
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "version": 2,
+                                        "data": (self._local + byte_offset, False)}
+
+        t = torch.as_tensor(_Raw(), device=self.device)
+        t._cgq_owner = self                # keep the allocation alive as long as the view is
+        return t
+
+    def close(self):
+        if getattr(self, "_local", None):
+            for p in self._opened:
+                self._lib.cgq_ipc_close(p)
+            self._lib.cgq_ipc_free(self._local)
+            self._local, self._opened = None, []
+
+
+class TpExchange:
+    """The device-side plumbing of one rank's tensor-parallel decode step: LL receive buffers for the row-parallel
+    linears, a peer-visible logits row for the broadcast lm_head, barrier flags, the error word.  Hands out the
+    `cgq_tp_ctx` hints for `cgq_tp_next` (include/cgq.h)."""
+
+    def __init__(self, hidden: int, vocab: int, step_counter: Tensor, group=None):
+        from . import _lib
+
+        self.max_n = int(hidden)
+        # layout of every rank's block: [LL words: 2 slots x world x hidden x 8 B][logits: vocab x 2 B][flags: 8 x 4 B][err 4 B]
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group)
+        self.ll_bytes = 2 * world * self.max_n * 8
+        self.logit_off = self.ll_bytes
+        self.flag_off = (self.logit_off + vocab * 2 + 255) // 256 * 256
+        self.err_off = self.flag_off + 64
+        self.mem = PeerMemory(self.err_off + 64, group)
+        self.world, self.rank = self.mem.world, self.mem.rank
+        self.step = step_counter                      # int32 device tensor, element 0 = token counter
+        self.logits = self.mem.tensor(torch.float16, vocab, self.logit_off)
+        self.err = self.mem.tensor(torch.int32, 1, self.err_off)
+        self._lib, self._TpCtx = _lib, _lib.TpCtx
+
+    def _ctx(self, reduce: bool, bcast_offset: int | None):
+        c = self._TpCtx()
+        c.world, c.rank, c.max_n = self.world, self.rank, self.max_n
+        c.out_offset = 0 if bcast_offset is None else int(bcast_offset)
+        for r in range(self.world):
+            c.recv[r] = self.mem.ptrs[r] if reduce else None
+            c.out[r] = (self.mem.ptrs[r] + self.logit_off) if bcast_offset is not None else None
+        c.step = self.step.data_ptr()
+        c.err = self.mem.ptrs[self.rank] + self.err_off
+        return c
+
+    def next_reduce(self, idx: int) -> None:
+        """The NEXT cgq_w4a16_gemv_fused launch of this thread is a row-parallel linear: exchange + sum its partials."""
+        import ctypes
+
+        self._lib.check(self._lib.load().cgq_tp_next(ctypes.byref(self._ctx(True, None)), idx))
+
+    def next_broadcast(self, column_offset: int) -> None:
+        """The NEXT launch stores its N columns into every rank's logits row at `column_offset`."""
+        import ctypes
+
+        self._lib.check(self._lib.load().cgq_tp_next(ctypes.byref(self._ctx(False, column_offset)), 0))
+
+    def barrier(self, stream: int) -> None:
+        import ctypes
+
+        arr = (ctypes.c_void_p * 8)(*[(self.mem.ptrs[r] + self.flag_off) for r in range(self.world)], *([None] * (8 - self.world)))
+        self._lib.check(self._lib.load().cgq_tp_barrier(arr, self.world, self.rank, self.step.data_ptr(),
+                                                       self.mem.ptrs[self.rank] + self.err_off, stream))
+
+    def error(self) -> int:
+        """0, or the epoch of an exchange whose peer words never arrived (synchronises)."""
+        return int(self.err.item())

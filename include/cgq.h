@@ -208,6 +208,43 @@ int cgq_program_status(uint64_t handle, int* workers, int* failed);
 int cgq_program_destroy(uint64_t handle);
 
 /*
+ * ---- Tensor parallelism of the fused decode step (no reference counterpart: the reference is single-GPU) ------
+ * One process per GPU.  Column-parallel linears (qkv_proj, w_in, lm_head) need no exchange; a ROW-parallel linear
+ * (o_proj, w_out: this rank holds a k-slice) exchanges its fp32 partial sums INSIDE the decode kernel's epilogue:
+ * every output column is stored as an 8-byte {value, epoch} word into every rank's receive buffer over NVLink
+ * (peer-mapped device memory, cgq_ipc_*), each rank then sums the `world` words of the column in rank order, rounds
+ * once and adds the residual -- no NCCL call, no extra launch, bit-identical rows on all ranks.
+ *   recv[r]   rank r's receive buffer, [2 slots][world][max_n] x 8 bytes, zero-initialised (recv[rank] = own)
+ *   step      device int32 incremented once per token BEFORE the step's launches run (cgq_decode_begin_w4 does it
+ *             to state[2]); epoch = step * 128 + idx + 1
+ *   err       device uint32, set if a peer's word never arrived (bounded spin), or NULL
+ *   out[r]    broadcast stores of a column-parallel linear (lm_head): rank r's full output buffer; this rank's N
+ *             columns go to out[r][out_offset + n] for every r.  NULL = plain local store to C.
+ * cgq_tp_next(ctx, idx): one-shot hint for the NEXT cgq_w4a16_gemv_fused launch of the calling thread; idx = running
+ * index of the exchange within the token (consecutive exchanges alternate slots), < 127.  For a broadcast-only launch
+ * pass recv[0] = NULL.  cgq_tp_barrier: a one-thread kernel that publishes `epoch` to every rank's `flags[rank]`
+ * (release, system scope) and waits until all `world` flags of its own array reached it -- run once after the
+ * broadcast linear so that the sampler sees every rank's logits.
+ */
+typedef struct {
+  int world, rank;
+  int max_n;
+  int out_offset;
+  void* recv[8];
+  const int* step;
+  uint32_t* err;
+  void* out[8];
+} cgq_tp_ctx;
+int cgq_tp_next(const cgq_tp_ctx* ctx, uint32_t idx);
+int cgq_tp_barrier(uint32_t* const* flags /*[world] peer-mapped, each [world] uint32*/, int world, int rank,
+                   const int* step, uint32_t* err, void* stream);
+/* Peer-visible device memory: cudaMalloc + legacy CUDA IPC handle (64 bytes) / open a peer's handle / close / free. */
+int cgq_ipc_alloc(size_t bytes, void** ptr, void* handle64);
+int cgq_ipc_open(const void* handle64, void** ptr);
+int cgq_ipc_close(void* ptr);
+int cgq_ipc_free(void* ptr);
+
+/*
  * ---- One-launch decode step ("step program"): embedding row + attention + linears of a whole token -----------
  * The batch-1 token step of the int4g32 model (ChatGLM2Model.forward with past_key_values, model.py:329-392) as ONE
  * persistent cooperative kernel: one CTA per SM, the TMA producer of every CTA streams the weights of the whole
@@ -260,6 +297,7 @@ int cgq_step_destroy(uint64_t handle);
  * (int4/qlinear.py:122-130) and the device-side position bookkeeping:
  *   state[1] = state[0]  (tokens in the KV cache before this step, used by cgq_decode_attention)
  *   state[0] += 1
+ *   state[2] += 1        (token counter: the epoch source of the tensor-parallel exchanges; state has >= 3 ints)
  * The host sets state[0] once after prefill; afterwards the step is a static CUDA graph.
  */
 int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq /*[V/2, D]*/, const void* scale,

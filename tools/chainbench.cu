@@ -216,7 +216,8 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&kc, kvb));
     CK(cudaMalloc(&vc, kvb));
     CK(cudaMalloc(&ids, 8));
-    CK(cudaMalloc(&state, 8));
+    CK(cudaMalloc(&state, 16));
+    CK(cudaMemset(state, 0, 16));
     fill_h<<<64, 256>>>(normw, H, 3, 0.8f, 1.2f);
     fill_h<<<64, 256>>>(freqs, (size_t)(MAXLEN + 2) * DH, 4, -1.f, 1.f);
     fill_h<<<592, 256>>>(kc, kvb / 2, 6, -1.f, 1.f);
