@@ -230,6 +230,7 @@ extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, 
         set_error("%s: tcgen05 kernel needs K%%32==0, N%%16==0, 16-byte aligned pointers, lda%%8==0", fn);
         return CGQ_ERR_MISALIGNED;
       }
+      if (workspace_bytes < kWorkspaceBytes) a.workspace = nullptr;   // no split-K without the partial-tile workspace
       return launch_w4_tc(a);
     case CGQ_IMPL_GEMV:
     case CGQ_IMPL_GEMV_EXACT:
@@ -340,6 +341,7 @@ extern "C" int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, c
         set_error("%s: tcgen05 kernel needs K%%16==0, 16-byte aligned pointers, lda%%8==0", fn);
         return CGQ_ERR_MISALIGNED;
       }
+      if (workspace_bytes < kWorkspaceBytes) a.workspace = nullptr;
       return launch_w8_tc(a);
     case CGQ_IMPL_GEMV:
       if (M > 8 || !w8_gemv_supported(a)) {

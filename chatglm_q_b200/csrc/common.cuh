@@ -70,7 +70,11 @@ constexpr int kMaxTiles = 8192;
 constexpr int kCounterStride = 32;  // ints: one 128-byte line per tile counter (atomics on one line serialise)
 constexpr size_t kCounterBytes = sizeof(int) * kCounterStride * kMaxTiles;
 constexpr size_t kSlotFloats = 8 * 128;  // M_MAX x BN
-constexpr size_t kWorkspaceBytes = kCounterBytes + sizeof(float) * kSlotFloats * 2 * kMaxCtas;
+constexpr size_t kStreamKBytes = sizeof(float) * kSlotFloats * 2 * kMaxCtas;
+// split-K partial tiles of the tcgen05 prefill kernel at small M (gemm_tc.cu): [items][128][MB] fp32
+constexpr size_t kPartialOffset = (kCounterBytes + kStreamKBytes + 1023) / 1024 * 1024;
+constexpr size_t kPartialBytes = 64u << 20;
+constexpr size_t kWorkspaceBytes = kPartialOffset + kPartialBytes;
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 struct GemmArgs {

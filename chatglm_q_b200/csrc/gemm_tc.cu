@@ -11,13 +11,15 @@
 //     with the 128-byte swizzle straight into its canonical UMMA layout; any token count > 8 maps to
 //     MB in {32, 64, 128, 256} without padding the 128-wide UMMA M.
 //
-// Warp roles (320 threads, persistent over (n-tile, token-block) tiles, weights of one n-tile are
+// Warp roles (448 threads, persistent over (n-tile, token-block[, k-split]) work items, weights of one n-tile are
 // shared through L2 by the CTAs working on its token blocks at the same time):
-//   warp 8      TMA producer: packed weights [32 x 128 B], scales [2 x 128], activations [MB x 64]
-//   warps 4-7   dequant: packed smem -> registers -> fp16/bf16 tile in the canonical MN-major
+//   warp 12     TMA producer: packed weights [32 x 128 B], scales [2 x 128], activations [MB x 64]
+//   warps 4-11  dequant (two per SM sub-partition: one warp per sub-partition left the pipeline at ~0.53 us per
+//               64-k stage whatever the token block, the tensor pipe needs 0.13 .. 0.27 us):
+//               packed smem -> registers -> fp16/bf16 tile in the canonical MN-major
 //               SWIZZLE_128B layout (reference rounding: (q-8) exact, one rounding in the multiply by
 //               the group scale), fence.proxy.async, mbarrier
-//   warp 9      one lane issues tcgen05.mma (cta_group::1, kind::f16, fp32 accumulators in TMEM),
+//   warp 13     one lane issues tcgen05.mma (cta_group::1, kind::f16, fp32 accumulators in TMEM),
 //               tcgen05.commit releases the smem stages; owns the TMEM allocation (2 accumulators)
 //   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 bit) -> round to T -> (+ bias, second rounding)
 //               -> C, overlapped with the next tile's MMAs through the second accumulator
@@ -25,6 +27,8 @@
 // The int8 variant (chatglm_q/int8/triton_ops.py:13-84) shares the skeleton: its weight is [N, K]
 // K-contiguous, so the dequantised tile (round_T(q * scale[n]), int8/qlinear.py:38) is a K-major A
 // operand; the packed stage is [128 n x 64 k] bytes and the per-channel scales come from global memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -34,9 +38,12 @@ namespace {
 
 constexpr int TN = 128;          // weight columns per tile  (UMMA M)
 constexpr int BK = 64;           // k per pipeline stage      (4 UMMA K-steps)
-constexpr int STAGES = 4;        // TMA ring depth
-constexpr int ABUFS = 2;         // dequantised-A double buffer
-constexpr int kThreads = 320;
+constexpr int MAX_STAGES = 12;   // TMA ring depth: as many stages as fit in shared memory, at most this
+constexpr int ABUFS = 4;         // dequantised-A ring: the dequant warps run up to 4 stages ahead of the MMAs (with 2, the
+                                 // store -> fence -> MMA -> commit -> mbarrier -> next store chain paced every stage at ~0.5 us)
+constexpr int kDeqWarps = 8;         // dequant warps (two per SM sub-partition)
+constexpr int kTmaWarp = 4 + kDeqWarps, kMmaWarp = kTmaWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int P_BYTES = (BK / 2) * TN;       // 4096: packed int4 tile
 constexpr int S_BYTES = (BK / 32) * TN * 2;  // 512: scale tile
 constexpr int PS_BYTES = 5120;               // packed + scales, padded to keep B tiles 1024-aligned
@@ -53,6 +60,13 @@ struct Params {
   int n_tiles, m_blocks, k_stages;
   uint32_t idesc;
   const void* scale8;   // int8 variant: per-channel scales [N]
+  // split-K (small M: fewer (n-tile, token-block) tiles than SMs): a work item is (tile, k-split); the splits of a
+  // tile run on different CTAs at the same time, write fp32 partial tiles to the workspace and the LAST one to arrive
+  // (per-tile counter) adds them in split order -- deterministic -- and runs the epilogue
+  int stages;           // TMA ring depth of this launch
+  int k_splits;
+  float* ws_part;       // [items][128][MB] fp32
+  int* ws_ctr;          // one counter per tile (128-byte stride), self-cleaning
 };
 
 // 64-bit shared-memory matrix descriptor (SWIZZLE_128B, Blackwell version 1).
@@ -152,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t stage_bytes = b_bytes + (kW8 ? P8_BYTES : PS_BYTES);
   // layout: A buffers | stages { B tile | packed | scales } | barriers | tmem ptr
   const uint32_t off_stage = ABUFS * A_BYTES;
+  const int STAGES = p.stages;
   const uint32_t off_bar = off_stage + STAGES * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + off_bar);
   uint64_t* full_tma = bars;                    // [STAGES]
@@ -163,11 +178,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.n_tiles * p.m_blocks;
+  const int total_tiles = p.n_tiles * p.m_blocks * p.k_splits;     // work items
   const uint32_t tmem_cols = (2 * MB <= 32) ? 32u : (2 * MB <= 64) ? 64u : (2 * MB <= 128) ? 128u
                              : (2 * MB <= 256) ? 256u : 512u;
 
-  if (threadIdx.x == 8 * 32) {
+  if (threadIdx.x == kTmaWarp * 32) {
     ptx::prefetch_tmap(&tmP);
     if (!kW8) ptx::prefetch_tmap(&tmS);
     ptx::prefetch_tmap(&tmA);
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&empty_tma[s], 1);
     }
     for (int b = 0; b < ABUFS; ++b) {
-      ptx::mbar_init(&a_full[b], 4);
+      ptx::mbar_init(&a_full[b], 4);      // the four warps of the group that owns the stage
       ptx::mbar_init(&a_empty[b], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -194,15 +209,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       const uint64_t pol_w = ptx::policy_evict_first();   // weights: streamed (re-use is in L2 window)
       const uint64_t pol_a = ptx::policy_evict_last();    // activations: re-read by every n-tile
       int s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / p.k_splits, sp = item - tile * p.k_splits;
         const int nt = tile / p.m_blocks, mb = tile - nt * p.m_blocks;
-        for (int ks = 0; ks < p.k_stages; ++ks) {
+        const int ks0 = p.k_stages * sp / p.k_splits, ks1 = p.k_stages * (sp + 1) / p.k_splits;
+        for (int ks = ks0; ks < ks1; ++ks) {
           ptx::mbar_wait(&empty_tma[s], ph ^ 1);
           uint8_t* st = gen + off_stage + s * stage_bytes;
           ptx::mbar_expect_tx(&full_tma[s], b_bytes + (kW8 ? P8_BYTES : P_BYTES + S_BYTES));
@@ -220,15 +237,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       int s = 0, ph = 0, ab = 0, aph = 0, acc = 0, cph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int sp = item % p.k_splits;
+        const int ks0 = p.k_stages * sp / p.k_splits, ks1 = p.k_stages * (sp + 1) / p.k_splits;
         ptx::mbar_wait(&acc_empty[acc], cph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * MB);
-        for (int ks = 0; ks < p.k_stages; ++ks) {
+        for (int ks = ks0; ks < ks1; ++ks) {
           ptx::mbar_wait(&full_tma[s], ph);
           ptx::mbar_wait(&a_full[ab], aph);
           ptx::tc_fence_after();
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                        : make_desc(a_addr + k4 * 2 * ATOM, (BK / 8) * ATOM, ATOM);
             // B: K-major rows of 128 B, 8-row atoms 1 KB apart; K-step = 32 B inside the row
             const uint64_t bdesc = make_desc(b_addr + k4 * 32, 16, ATOM);
-            ptx::umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (ks | k4) != 0 ? 1u : 0u);
+            ptx::umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (ks != ks0 || k4 != 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_tma[s]);   // stage (activations + packed) reusable when MMAs retire
           ptx::umma_commit(&a_empty[ab]);
@@ -267,14 +286,34 @@ __global__ void __launch_bounds__(kThreads, 1)
     // thread -> (16-byte output chunk c of 8 columns, packed rows r0 + 8 i); 128 threads cover
     // 32 packed rows x 16 chunks.  Chunk element order is (c0,c2,c1,c3,c4,c6,c5,c7): the epilogue
     // un-permutes the TMEM lanes.
-    const int t = threadIdx.x - 128;
+    // Two groups of four warps take ALTERNATE stages: one group's store -> fence -> arrive chain of a stage overlaps
+    // the other group's loads and conversions of the next one (a single group paced the pipeline at ~0.5 us per
+    // stage whatever the token block).  Inside a group: thread -> (16-byte output chunk c of 8 columns, packed rows
+    // r0 + 8 i); 128 threads cover 32 packed rows x 16 chunks.  Chunk element order is (c0,c2,c1,c3,c4,c6,c5,c7):
+    // the epilogue un-permutes the TMEM lanes.
+    const int grp = (warp - 4) >> 2;
+    const int t = (threadIdx.x - 128) & 127;
     int s = 0, ph = 0, ab = 0, aph = 0;
+    unsigned stage_no = 0;
+    auto advance = [&]() {
+      ++stage_no;
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+      if (++ab == ABUFS) {
+        ab = 0;
+        aph ^= 1;
+      }
+    };
     if constexpr (kW8) {
       // thread -> (16-byte chunk j = 8 consecutive k, weight rows r0 + 16 i): 128 rows x 8 chunks
       const int j = t & 7, r0 = t >> 3;
       const T* sc = static_cast<const T*>(p.scale8);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / p.k_splits, sp = item - tile * p.k_splits;
         const int nt = tile / p.m_blocks;
+        const int n_ks = p.k_stages * (sp + 1) / p.k_splits - p.k_stages * sp / p.k_splits;
         uint32_t s2[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -286,7 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           cv.h[0] = cv.h[1] = (n < p.N) ? sc[n] : DT<T>::from_f(0.f);
           s2[i] = cv.u;
         }
-        for (int ks = 0; ks < p.k_stages; ++ks) {
+        for (int ks = 0; ks < n_ks; ++ks, advance()) {
+          if (static_cast<int>(stage_no & 1u) != grp) continue;
           ptx::mbar_wait(&full_tma[s], ph);
           const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
           uint32_t out[8][4];
@@ -307,30 +347,25 @@ __global__ void __launch_bounds__(kThreads, 1)
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1;
-          }
-          if (++ab == ABUFS) {
-            ab = 0;
-            aph ^= 1;
-          }
         }
       }
     } else {
       const int c = t & 15;          // column chunk: columns 8c .. 8c+7
       const int r0 = t >> 4;         // 0..7
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int ks = 0; ks < p.k_stages; ++ks) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int sp = item % p.k_splits;
+        const int n_ks = p.k_stages * (sp + 1) / p.k_splits - p.k_stages * sp / p.k_splits;
+        for (int ks = 0; ks < n_ks; ++ks, advance()) {
+          if (static_cast<int>(stage_no & 1u) != grp) continue;
           ptx::mbar_wait(&full_tma[s], ph);
           const uint32_t st = base + off_stage + s * stage_bytes + b_bytes;
           uint32_t out[4][8];  // [row i][k parity * 4 + word]
-  #pragma unroll
+#pragma unroll
           for (int g = 0; g < 2; ++g) {
             const uint4 sv = ptx::lds128(st + P_BYTES + g * (TN * 2) + c * 16);
             const uint32_t s02a = __byte_perm(sv.x, sv.y, 0x5410), s13a = __byte_perm(sv.x, sv.y, 0x7632);
             const uint32_t s02b = __byte_perm(sv.z, sv.w, 0x5410), s13b = __byte_perm(sv.z, sv.w, 0x7632);
-  #pragma unroll
+#pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int i = 2 * g + h;                 // packed row r0 + 8 i  (rows 0..15 = group 0)
               const uint2 pk = ptx::lds64(st + (r0 + 8 * i) * TN + c * 8);
@@ -340,9 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           ptx::mbar_wait(&a_empty[ab], aph ^ 1);
           const uint32_t a_addr = base + ab * A_BYTES + (c >> 3) * ((BK / 8) * ATOM);
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 4; ++i) {
-  #pragma unroll
+#pragma unroll
             for (int par = 0; par < 2; ++par) {
               const int k = 2 * (r0 + 8 * i) + par;    // k row inside the stage
               const uint32_t addr = a_addr + (k >> 3) * ATOM + (k & 7) * 128 + (((c & 7) ^ (k & 7)) << 4);
@@ -353,14 +388,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&a_full[ab]);
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1;
-          }
-          if (++ab == ABUFS) {
-            ab = 0;
-            aph ^= 1;
-          }
         }
       }
     }
@@ -372,7 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // int4: (0,2,1,3) un-permute of the dequant chunk order; int8: identity
     const int col_in_tile = kW8 ? row : ((row & ~3) | ((row & 1) << 1) | ((row >> 1) & 1));
     int acc = 0, cph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);      // epilogue warps' broadcast word (shared memory)
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      const int tile = item / p.k_splits;
       const int nt = tile / p.m_blocks, mb = tile - nt * p.m_blocks;
       const int n = nt * TN + col_in_tile;
       const int m0 = mb * MB;
@@ -380,11 +409,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) +
                              static_cast<uint32_t>(acc * MB);
+      // partial tile layout [item][16-token chunk][128 rows][16 floats]: a warp writes 2 KB contiguous per chunk
+      float* part = p.k_splits > 1 ? p.ws_part + static_cast<size_t>(item) * TN * MB + row * 16 : nullptr;
       for (int c0 = 0; c0 < MB; c0 += 16) {
         uint32_t v[16];
         ptx::tmem_ld_32x32b_x16(taddr + c0, v);
         ptx::tmem_ld_wait();
-        if (n < p.N) {
+        if (part != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(part + c0 * TN + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else if (n < p.N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = m0 + c0 + j;
@@ -399,12 +434,66 @@ __global__ void __launch_bounds__(kThreads, 1)
         acc = 0;
         cph ^= 1;
       }
+      if (p.k_splits > 1) {
+        // the last split of this tile to arrive adds all partial tiles in split order and stores the result
+        __threadfence();
+        ptx::named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+          int* ctr = p.ws_ctr + static_cast<size_t>(tile) * kCounterStride;
+          const int old = atomicAdd(ctr, 1);
+          if (old == p.k_splits - 1) *ctr = 0;      // self-cleaning for the next launch
+          *last_flag = old;
+        }
+        ptx::named_bar_sync(1, 128);
+        const bool last = *last_flag == p.k_splits - 1;
+        ptx::named_bar_sync(1, 128);                // (the flag word is rewritten by the next item)
+        if (last) {
+          __threadfence();
+          const float* p0 = p.ws_part + static_cast<size_t>(tile) * p.k_splits * TN * MB + row * 16;
+          for (int c0 = 0; c0 < MB; c0 += 16) {
+            // all splits' 16 values of this row in flight at once (16 independent 16-byte loads at 4 splits)
+            float4 t[4][4];
+#pragma unroll
+            for (int sp = 0; sp < 4; ++sp) {
+              if (sp < p.k_splits) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                               : "=f"(t[sp][q].x), "=f"(t[sp][q].y), "=f"(t[sp][q].z), "=f"(t[sp][q].w)
+                               : "l"(p0 + static_cast<size_t>(sp) * TN * MB + c0 * TN + 4 * q));
+              }
+            }
+            float vv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vv[j] = 0.f;
+#pragma unroll
+            for (int sp = 0; sp < 4; ++sp) {
+              if (sp < p.k_splits) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  vv[4 * q] += t[sp][q].x;
+                  vv[4 * q + 1] += t[sp][q].y;
+                  vv[4 * q + 2] += t[sp][q].z;
+                  vv[4 * q + 3] += t[sp][q].w;
+                }
+              }
+            }
+            if (n < p.N) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int m = m0 + c0 + j;
+                if (m < p.M) Cp[static_cast<int64_t>(m) * p.ldc + n] = epilogue<T>(vv[j], bias, n);
+              }
+            }
+          }
+        }
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 template <typename T, bool kW8>
@@ -422,6 +511,40 @@ int launch_t(const GemmArgs& a) {
   prm.m_blocks = (a.M + MB - 1) / MB;
   prm.k_stages = (a.K + BK - 1) / BK;
   prm.scale8 = a.scale;
+  // split-K when the tiles alone leave SMs idle: the smallest split count (<= 8, >= 4 k-stages per split) whose
+  // last wave is >= 85 % full (at most 4: the fix-up keeps all splits' values in registers), bounded by the workspace
+  prm.k_splits = 1;
+  prm.ws_part = nullptr;
+  prm.ws_ctr = nullptr;
+  {
+    static const int forced = [] {
+      const char* e = getenv("CGQ_TC_SPLITS");
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    const int tiles = prm.n_tiles * prm.m_blocks, sms = sm_count();
+    const size_t tile_bytes = static_cast<size_t>(TN) * MB * sizeof(float);
+    auto eff = [&](int ks) {
+      const int items = tiles * ks, waves = (items + sms - 1) / sms;
+      return static_cast<double>(items) / (static_cast<double>(waves) * sms);
+    };
+    int best = 1;
+    if (a.workspace != nullptr && tiles <= kMaxTiles && eff(1) < 0.5) {      // (measured: with a wave >= half full the
+                                                                             // fix-up costs more than the split buys)
+      for (int ks = 2; ks <= 4; ++ks) {
+        if (prm.k_stages / ks < 4 || static_cast<size_t>(tiles) * ks * tile_bytes > kPartialBytes) break;
+        if (eff(ks) > eff(best) + 0.02) best = ks;
+        if (eff(best) >= 0.9) break;
+      }
+    }
+    if (forced >= 1 && forced <= 4 && a.workspace != nullptr &&
+        static_cast<size_t>(tiles) * forced * tile_bytes <= kPartialBytes && forced <= prm.k_stages)
+      best = forced;
+    if (best > 1) {
+      prm.k_splits = best;
+      prm.ws_ctr = static_cast<int*>(a.workspace);
+      prm.ws_part = reinterpret_cast<float*>(static_cast<char*>(a.workspace) + kPartialOffset);
+    }
+  }
   const uint32_t fmt = (DT<T>::code == CGQ_DTYPE_F16) ? 0u : 1u;
   // c=F32 | a,b format | A major (int4: MN, int8: K) | B K-major | N = MB | M = 128
   prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kW8 ? 0u : 1u) << 15) | (0u << 16) |
@@ -455,9 +578,18 @@ int launch_t(const GemmArgs& a) {
   rc = get_tmap_2d(ka, &tmA);
   if (rc != CGQ_OK) return rc;
 
-  const size_t smem = 1024 + ABUFS * A_BYTES +
-                      static_cast<size_t>(STAGES) * (MB * 128 + (kW8 ? P8_BYTES : PS_BYTES)) +
-                      8 * (2 * STAGES + 2 * ABUFS + 4) + 16;
+  // the per-CTA pipeline is bound by (stages in flight) / (TMA round-trip latency): take every stage that fits
+  const size_t stage_b = static_cast<size_t>(MB) * 128 + (kW8 ? P8_BYTES : PS_BYTES);
+  const size_t fixed_b = 1024 + ABUFS * A_BYTES + 8 * (2 * MAX_STAGES + 2 * ABUFS + 4) + 32;
+  int stages = static_cast<int>((232448 - fixed_b) / stage_b);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  static const int st_env = [] {
+    const char* e = getenv("CGQ_TC_STAGES");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (st_env >= 2 && st_env < stages) stages = st_env;
+  prm.stages = stages;
+  const size_t smem = fixed_b + static_cast<size_t>(stages) * stage_b;
   auto kern = wq_gemm_tc_kernel<T, kW8>;
   static size_t configured[64] = {0};
   int dev = 0;
@@ -467,7 +599,7 @@ int launch_t(const GemmArgs& a) {
                                       static_cast<int>(smem)));
     configured[dev] = smem;
   }
-  int grid = prm.n_tiles * prm.m_blocks;
+  int grid = prm.n_tiles * prm.m_blocks * prm.k_splits;
   if (grid > sm_count()) grid = sm_count();
   kern<<<grid, kThreads, smem, a.stream>>>(tmP, tmS, tmA, prm);
   CGQ_CUDA_TRY(cudaGetLastError());
