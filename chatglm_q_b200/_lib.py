@@ -24,6 +24,9 @@ SYMBOLS = {
     "cgq_debug_trace": (None, [c_void_p]),
     "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "cgq_w8a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_void_p, c_float, c_void_p]),
+    "cgq_decode_begin_w8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cgq_handover_next": (c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
     "cgq_w4_gemv_tiles": (c_int, [c_int]),
     "cgq_program_create": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -313,6 +313,32 @@ extern "C" int cgq_w4a16_gemv_fused(const void* A, const uint8_t* Wq, const void
   return launch_w4_gemv_fused(a, fu);
 }
 
+extern "C" int cgq_w8a16_gemv_fused(const void* A, const int8_t* Wq, const void* scale, const void* bias,
+                                    const void* resid, void* C, int N, int K, int dtype, int prologue,
+                                    const void* norm_w, float eps, void* stream) {
+  const char* fn = "cgq_w8a16_gemv_fused";
+  const int a_len = prologue == CGQ_PRO_SILU_GATE ? 2 * K : K;
+  int rc = check_common(fn, A, a_len, Wq, scale, C, N, 1, N, K, dtype);
+  if (rc != CGQ_OK) return rc;
+  if (prologue != CGQ_PRO_NONE && prologue != CGQ_PRO_RMSNORM && prologue != CGQ_PRO_SILU_GATE) {
+    set_error("%s: unknown prologue %d", fn, prologue);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  if (prologue == CGQ_PRO_RMSNORM && (norm_w == nullptr || (reinterpret_cast<uintptr_t>(norm_w) & 15))) {
+    set_error("%s: CGQ_PRO_RMSNORM needs a 16-byte aligned norm weight", fn);
+    return CGQ_ERR_MISALIGNED;
+  }
+  rc = check_device();
+  if (rc != CGQ_OK) return rc;
+  GemmArgs a{A, a_len, Wq, scale, bias, C, N, 1, N, K, dtype, nullptr, static_cast<cudaStream_t>(stream)};
+  if (!w8_gemv_supported(a)) {
+    set_error("%s: needs K%%16==0 and 16-byte aligned A / Wq", fn);
+    return CGQ_ERR_MISALIGNED;
+  }
+  GemvFused fu{prologue, norm_w, eps, resid};
+  return launch_w8_gemv_fused(a, fu);
+}
+
 extern "C" int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, const void* scale,
                                  const void* bias, void* C, int64_t ldc, int M, int N, int K,
                                  int dtype, void* workspace, size_t workspace_bytes, void* stream,

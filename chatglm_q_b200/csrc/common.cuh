@@ -109,6 +109,7 @@ int launch_w8_simple(const GemmArgs& a);
 int launch_w4_gemv(const GemmArgs& a, bool exact);
 int launch_w4_gemv_umma(const GemmArgs& a, bool* taken);
 int launch_w8_gemv(const GemmArgs& a);
+int launch_w8_gemv_fused(const GemmArgs& a, const GemvFused& fu);
 int launch_w4_tc(const GemmArgs& a);
 bool w4_tc_supported(const GemmArgs& a);
 int launch_w8_tc(const GemmArgs& a);

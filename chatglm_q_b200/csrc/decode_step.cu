@@ -53,6 +53,27 @@ __global__ void __launch_bounds__(256)
   if (d < D) x[d] = dequant4<T>((wrow[d] >> shift) & 0xF, srow[d]);
 }
 
+// int8 QEmbedding row (int8/qlinear.py:118-120, scales are per embedding column): x[d] = round_T(q[t, d] * scale[d])
+template <typename T>
+__global__ void __launch_bounds__(256)
+    decode_begin_w8_kernel(const int64_t* __restrict__ ids, const int8_t* __restrict__ Wq, const T* __restrict__ scale,
+                           T* __restrict__ x, int V, int D, int* __restrict__ state) {
+  ptx::pdl_wait_prior_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int cur = state[0];
+    state[1] = cur;
+    state[0] = cur + 1;
+    state[2] = state[2] + 1;
+    __threadfence();
+  }
+  __syncthreads();
+  ptx::pdl_launch_dependents();
+  int64_t t = ids[0];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) x[d] = dequant8<T>(Wq[t * D + d], scale[d]);
+}
+
 // ------------------------------------------------------------------ decode_attn
 struct AttnParams {
   const void* qkv;     // [n_head*DH | n_groups*DH | n_groups*DH]
@@ -408,6 +429,24 @@ extern "C" int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq, const 
                       static_cast<const __nv_bfloat16*>(scale), static_cast<__nv_bfloat16*>(x), V, D,
                       group, state);
   set_error("cgq_decode_begin_w4: bad dtype %d", dtype);
+  return CGQ_ERR_BAD_DTYPE;
+}
+
+extern "C" int cgq_decode_begin_w8(const int64_t* ids, const int8_t* Wq, const void* scale, void* x, int V, int D,
+                                   int dtype, int* state, void* stream) {
+  if (V <= 0 || D <= 0 || ids == nullptr || Wq == nullptr || scale == nullptr || x == nullptr || state == nullptr) {
+    set_error("cgq_decode_begin_w8: bad arguments V=%d D=%d", V, D);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((D + 255) / 256), block(256);
+  if (dtype == CGQ_DTYPE_F16)
+    return launch_pdl(decode_begin_w8_kernel<__half>, grid, block, 0, st, ids, Wq, static_cast<const __half*>(scale),
+                      static_cast<__half*>(x), V, D, state);
+  if (dtype == CGQ_DTYPE_BF16)
+    return launch_pdl(decode_begin_w8_kernel<__nv_bfloat16>, grid, block, 0, st, ids, Wq,
+                      static_cast<const __nv_bfloat16*>(scale), static_cast<__nv_bfloat16*>(x), V, D, state);
+  set_error("cgq_decode_begin_w8: bad dtype %d", dtype);
   return CGQ_ERR_BAD_DTYPE;
 }
 

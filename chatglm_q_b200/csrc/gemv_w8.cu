@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
+#include "w4_dev.cuh"
 
 namespace cgq {
 namespace {
@@ -342,6 +343,288 @@ int launch_t(const GemmArgs& a) {
   return launch_inst<T, false>(a, tmW, prm, grid, smem, pdl);
 }
 
+
+// =====================================================================================================
+// M == 1 int8 decode kernel on gemv_w4.cu's skeleton (round 2): (64-column tile) x (Z contiguous k-bands), the Z
+// CTAs of a tile form a thread-block cluster and reduce their band sums through distributed shared memory; the
+// TMA ring carries weights only, the activation band is staged once per CTA by the consumer warps through the
+// fused prologue (RMSNorm / SiLU*gate), the residual is added in the epilogue (cgq_w8a16_gemv_fused).  Replaces
+// the stream-K workspace fix-up for one token: qkv / o_proj took 11.6 - 11.9 us with it.
+namespace m1 {
+
+using w4::ldcg128;
+using w4::ldnc128;
+using w4::PRO_NONE;
+using w4::PRO_RMSNORM;
+using w4::PRO_SILU_GATE;
+
+struct P1 {
+  const void* A;
+  const void* scale;
+  const void* bias;
+  const void* resid;
+  const void* norm_w;
+  void* C;
+  int N, K, SPT, Z, S, band_units;
+  float eps;
+};
+
+template <typename T, int kPro>
+__global__ void __launch_bounds__(kThreads, 4)
+    w8_gemv_m1_kernel(const __grid_constant__ CUtensorMap tmW, const P1 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int S = p.S, Z = p.Z;
+  const uint32_t Wsm = base;
+  const uint32_t off_x = S * W_BYTES;
+  float* xred = reinterpret_cast<float*>(gen + off_x);                      // [Z][64] band sums (used on rank 0)
+  float* sred = xred + 8 * BN8;                                             // [CW] sum(x^2) partials
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_x + 8 * BN8 * 4 + 64);
+  uint64_t* empty = full + S;
+  const uint32_t Aband = base + ((off_x + 8 * BN8 * 4 + 64 + 16 * S + 15) & ~15u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;
+  const int u0 = p.SPT * z / Z, u1 = p.SPT * (z + 1) / Z;
+  const int n_units = u1 - u0;
+  const T* A = static_cast<const T*>(p.A);
+
+  if (threadIdx.x == CW * 32) {
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], CW);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  __syncthreads();
+  if (Z > 1) ptx::cluster_arrive_release();      // phase A: waited for before the first DSMEM store
+  ptx::pdl_launch_dependents();
+
+  if (warp == CW) {
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      auto issue = [&](int i, int slot) {
+        ptx::mbar_expect_tx(&full[slot], W_BYTES);
+        ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, (u0 + i) * KSTAGE, tile * BN8, &full[slot], pol);
+      };
+      const int prefill = min(n_units, S);
+      for (int i = 0; i < prefill; ++i) issue(i, i);        // weights do not depend on the previous kernel
+      int slot = 0, phase = 1;
+      for (int i = prefill; i < n_units; ++i) {
+        ptx::mbar_wait(&empty[slot], phase ^ 1);
+        issue(i, slot);
+        if (++slot == S) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+    if (Z > 1) ptx::cluster_wait_acquire();
+  } else {
+    // ---- stage the activation band (16-byte chunks of 8 k, zero beyond K) through the fused prologue
+    const int tid = threadIdx.x;
+    const int nchunk = p.K >> 3;
+    const int c_lo = u0 * (KSTAGE / 8), c_hi = u1 * (KSTAGE / 8);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    if (kPro == PRO_RMSNORM) {
+      const T* nw = static_cast<const T*>(p.norm_w);
+      ptx::pdl_wait_prior_grid();
+      float ss = 0.f;
+      for (int c = tid; c < nchunk; c += CW * 32) ss += w4::sumsq8<T>(ldcg128(A + c * 8));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) sred[warp] = ss;
+      ptx::named_bar_sync(1, CW * 32);
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < CW; ++w) tot += sred[w];
+      const float rstd = rsqrtf(tot / static_cast<float>(p.K) + p.eps);
+      for (int c = c_lo + tid; c < c_hi; c += CW * 32)
+        ptx::sts128(Aband + (c - c_lo) * 16,
+                    c < nchunk ? w4::rmsnorm8<T>(ldcg128(A + c * 8), ldnc128(nw + c * 8), rstd) : zero);
+    } else {
+      ptx::pdl_wait_prior_grid();
+      for (int c = c_lo + tid; c < c_hi; c += CW * 32) {
+        uint4 v = zero;
+        if (c < nchunk) {
+          v = ldcg128(A + c * 8);
+          if (kPro == PRO_SILU_GATE) v = w4::silu_gate8<T>(v, ldcg128(A + p.K + c * 8));
+        }
+        ptx::sts128(Aband + (c - c_lo) * 16, v);
+      }
+    }
+    ptx::named_bar_sync(1, CW * 32);
+
+    const int g = lane >> 2, tig = lane & 3;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    int slot = 0, phase = 0;
+    for (int it = 0; it < n_units; ++it) {
+      ptx::mbar_wait(&full[slot], phase);
+      const uint32_t wa = Wsm + slot * W_BYTES + (16 * warp + g) * KSTAGE;  // row g of this warp
+      const uint32_t wb = wa + 8 * KSTAGE;                                   // row g + 8
+      const uint32_t arow = Aband + (it * KSTAGE + 32 * tig) * 2;
+      uint32_t ld_dep = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = 2 * tig + h;  // 16-byte run: k = 16*chunk .. +15
+        const uint4 qa = ptx::lds128(wa + ((chunk ^ g) << 4));
+        const uint4 qb = ptx::lds128(wb + ((chunk ^ g) << 4));
+        uint4 a0 = zero, a1 = zero;
+        if (g == 0) {                       // one token: only MMA column 0 carries data
+          a0 = ptx::lds128(arow + 32 * h);
+          a1 = ptx::lds128(arow + 32 * h + 16);
+        }
+        ld_dep |= qa.x | qb.x;
+        const uint32_t wqa[4] = {qa.x, qa.y, qa.z, qa.w};
+        const uint32_t wqb[4] = {qb.x, qb.y, qb.z, qb.w};
+        const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t fr[4];
+          Cvt8<T>::run(wqa[e], fr[0], fr[2]);
+          Cvt8<T>::run(wqb[e], fr[1], fr[3]);
+          if (e & 1)
+            ptx::mma_16816(acc2, fr, av[2 * e], av[2 * e + 1], acc2, T());
+          else
+            ptx::mma_16816(acc, fr, av[2 * e], av[2 * e + 1], acc, T());
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_after_loads(&empty[slot], ld_dep, static_cast<uint32_t>(p.K) >> 31);
+      if (++slot == S) {
+        slot = 0;
+        phase ^= 1;
+      }
+    }
+    // D fragment, token 0 (lanes tig == 0): acc[0] = column 16 w + g, acc[2] = column 16 w + g + 8
+    const float v0 = acc[0] + acc2[0], v1 = acc[2] + acc2[2];
+    const int c0 = 16 * warp + g, c1 = c0 + 8;
+    auto finish = [&](float v, int col) {
+      const int n = tile * BN8 + col;
+      if (n < p.N) {
+        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+        static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(v * s, static_cast<const T*>(p.bias), n),
+                                                   static_cast<const T*>(p.resid), n);
+      }
+    };
+    if (Z == 1) {
+      if (tig == 0) {
+        finish(v0, c0);
+        finish(v1, c1);
+      }
+    } else {
+      ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
+      if (tig == 0) {
+        const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>(z * BN8) * 4u;
+        const uint32_t remote = ptx::mapa_rank(local, 0);
+        ptx::st_cluster_f32(remote + c0 * 4, v0);
+        ptx::st_cluster_f32(remote + c1 * 4, v1);
+      }
+    }
+  }
+  if (Z > 1) {
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    if (z == 0 && threadIdx.x < BN8) {
+      const int t = threadIdx.x, n = tile * BN8 + t;
+      if (n < p.N) {
+        float acc = 0.f;
+        for (int zz = 0; zz < Z; ++zz) acc += xred[zz * BN8 + t];       // rank order: deterministic
+        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+        static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(acc * s, static_cast<const T*>(p.bias), n),
+                                                   static_cast<const T*>(p.resid), n);
+      }
+    }
+  }
+}
+
+template <typename T, int kPro>
+int launch_pro(const GemmArgs& a, const CUtensorMap& tmW, const P1& prm, int grid, bool pdl) {
+  const size_t smem = 1024 + static_cast<size_t>(prm.S) * W_BYTES + 8 * BN8 * 4 + 64 + 16 * prm.S + 32 +
+                      static_cast<size_t>(prm.band_units) * KSTAGE * 2;
+  auto kern = w8_gemv_m1_kernel<T, kPro>;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CGQ_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured[dev] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (prm.Z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(prm.Z);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmW, prm));
+  return CGQ_OK;
+}
+
+template <typename T>
+int launch(const GemmArgs& a, const GemvFused* fu) {
+  static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
+  const int SPT = (a.K + KSTAGE - 1) / KSTAGE;
+  const int tiles = (a.N + BN8 - 1) / BN8;
+  const int slots = 4 * sm_count();
+  int Z = 1;
+  while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
+  const int grid = tiles * Z;
+  const int per_cta = (SPT + Z - 1) / Z;
+  int stages = grid * 4 <= slots * 3 ? 6 : 4;
+  if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
+  CUtensorMap tmW;
+  TmapKey kw{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K), KSTAGE, BN8,
+             CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_128B};
+  int rc = get_tmap_2d(kw, &tmW);
+  if (rc != CGQ_OK) return rc;
+  P1 prm;
+  prm.A = a.A;
+  prm.scale = a.scale;
+  prm.bias = a.bias;
+  prm.resid = fu != nullptr ? fu->resid : nullptr;
+  prm.norm_w = fu != nullptr ? fu->norm_w : nullptr;
+  prm.eps = fu != nullptr ? fu->eps : 0.f;
+  prm.C = a.C;
+  prm.N = a.N;
+  prm.K = a.K;
+  prm.SPT = SPT;
+  prm.Z = Z;
+  prm.S = stages;
+  prm.band_units = per_cta;
+  const int pro = fu != nullptr ? fu->prologue : PRO_NONE;
+  switch (pro) {
+    case PRO_RMSNORM:
+      return launch_pro<T, PRO_RMSNORM>(a, tmW, prm, grid, pdl);
+    case PRO_SILU_GATE:
+      return launch_pro<T, PRO_SILU_GATE>(a, tmW, prm, grid, pdl);
+    default:
+      return launch_pro<T, PRO_NONE>(a, tmW, prm, grid, pdl);
+  }
+}
+
+}  // namespace m1
+
 }  // namespace
 
 bool w8_gemv_supported(const GemmArgs& a) {
@@ -352,7 +635,15 @@ bool w8_gemv_supported(const GemmArgs& a) {
 }
 
 int launch_w8_gemv(const GemmArgs& a) {
+  static const bool legacy = env_int("CGQ_W8_STREAMK_M1", 0, 0, 1) != 0;    // the round-1 stream-K path for one token
+  if (a.M == 1 && !legacy)
+    return a.dtype == CGQ_DTYPE_F16 ? m1::launch<__half>(a, nullptr) : m1::launch<__nv_bfloat16>(a, nullptr);
   return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a) : launch_t<__nv_bfloat16>(a);
+}
+
+// M == 1 with a fused prologue (RMSNorm / SiLU-gate on the activation) and residual epilogue.
+int launch_w8_gemv_fused(const GemmArgs& a, const GemvFused& fu) {
+  return a.dtype == CGQ_DTYPE_F16 ? m1::launch<__half>(a, &fu) : m1::launch<__nv_bfloat16>(a, &fu);
 }
 
 }  // namespace cgq

@@ -54,6 +54,12 @@ def _is_w4_linear(m) -> bool:
             and s.dim() == 2 and s.shape[1] == w.shape[1] and w.shape[0] * 2 == s.shape[0] * 32)
 
 
+def _is_w8_linear(m) -> bool:
+    w, s = getattr(m, "weight", None), getattr(m, "weight_scale", None)
+    return (isinstance(w, Tensor) and isinstance(s, Tensor) and w.dtype == torch.int8 and w.dim() == 2
+            and s.dim() == 1 and s.shape[0] == w.shape[0])
+
+
 class FusedDecodeModel:
     def __init__(self, model: torch.nn.Module, max_len: int = 1024, handover: bool | None = None,
                  speculate: bool = False, last_logits_only: bool = False, alias_logits: bool | None = None,
@@ -105,12 +111,22 @@ class FusedDecodeModel:
         lins = [model.lm_head]
         for layer in model.layers:
             lins += [layer.attn.qkv_proj, layer.attn.o_proj, layer.ffn.w_in, layer.ffn.w_out]
-        if not all(_is_w4_linear(m) for m in lins):
-            raise TypeError("FusedDecodeModel needs the int4g32 model (uint8 [K/2,N] weights, [K/32,N] scales)")
         emb = model.word_embedding
-        if not (isinstance(getattr(emb, "weight", None), Tensor) and emb.weight.dtype == torch.uint8
-                and hasattr(emb, "weight_scale")):
-            raise TypeError("FusedDecodeModel needs the int4 QEmbedding word_embedding")
+        ew = getattr(emb, "weight", None)
+        if all(_is_w4_linear(m) for m in lins):
+            self.kind = "w4"           # int4g32: uint8 [K/2, N] weights, [K/32, N] scales (int4/qlinear.py:75-108)
+            if not (isinstance(ew, Tensor) and ew.dtype == torch.uint8 and hasattr(emb, "weight_scale")):
+                raise TypeError("FusedDecodeModel needs the int4 QEmbedding word_embedding with the int4g32 model")
+        elif all(_is_w8_linear(m) for m in lins):
+            self.kind = "w8"           # int8 per channel: int8 [N, K] weights, [N] scales (int8/qlinear.py:77-107)
+            if not (isinstance(ew, Tensor) and ew.dtype == torch.int8 and hasattr(emb, "weight_scale")
+                    and emb.weight_scale.dim() == 1):
+                raise TypeError("FusedDecodeModel needs the int8 QEmbedding word_embedding with the int8 model")
+        else:
+            raise TypeError("FusedDecodeModel needs the int4g32 model (uint8 [K/2,N] weights, [K/32,N] scales) or the "
+                            "int8 model (int8 [N,K] weights, [N] scales), not a mix")
+        if self.kind != "w4":
+            self.one_launch = False
         dt = model.lm_head.weight_scale.dtype
         if dt not in _DTYPE_CODE:
             raise TypeError(f"FusedDecodeModel computes in float16 / bfloat16, model is {dt}")
@@ -162,16 +178,24 @@ class FusedDecodeModel:
     def _gemv(self, lib, stream, lin, a, out, prologue=PRO_NONE, norm=None, resid=None, nxt=None,
               wait=None, signal=None):
         k2, n = lin.weight.shape
-        if self.handover and (wait is not None or signal is not None):
+        if self.kind == "w4" and self.handover and (wait is not None or signal is not None):
             # wait = (counter row, producing linear): poll until all of ITS output tiles are announced
             _lib.check(lib.cgq_handover_next(
                 None if wait is None else self.ctr[wait[0]].data_ptr(),
                 0 if wait is None else lib.cgq_w4_gemv_tiles(wait[1].weight.shape[1]),
                 None if signal is None else self.ctr[signal].data_ptr()))
-        if nxt is not None and self.hints:   # experimental L2 prefetch of the NEXT linear's weights (CGQ_PF_MB)
+        if self.kind == "w4" and nxt is not None and self.hints:   # experimental L2 prefetch of the NEXT linear's weights (CGQ_PF_MB)
             _lib.check(lib.cgq_prefetch_next_w4(nxt.weight.data_ptr(), nxt.weight_scale.data_ptr(),
                                                 nxt.weight.shape[1], nxt.weight.shape[0] * 2))
         bias = lin.bias if getattr(lin, "bias", None) is not None else None
+        if self.kind == "w8":
+            n8, k8 = lin.weight.shape
+            _lib.check(lib.cgq_w8a16_gemv_fused(
+                a.data_ptr(), lin.weight.data_ptr(), lin.weight_scale.data_ptr(),
+                None if bias is None else bias.data_ptr(), None if resid is None else resid.data_ptr(), out.data_ptr(),
+                n8, k8, self.code, prologue, None if norm is None else norm.weight.data_ptr(),
+                float(norm.eps) if norm is not None else 0.0, stream))
+            return
         _lib.check(lib.cgq_w4a16_gemv_fused(
             a.data_ptr(), lin.weight.data_ptr(), lin.weight_scale.data_ptr(),
             None if bias is None else bias.data_ptr(), None if resid is None else resid.data_ptr(),
@@ -244,9 +268,14 @@ class FusedDecodeModel:
             _lib.check(lib.cgq_step_run(self._step_handle, stream))
             return
         emb = m.word_embedding
-        _lib.check(lib.cgq_decode_begin_w4(
-            self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
-            emb.weight.shape[0] * 2, emb.weight.shape[1], 32, self.code, self.state.data_ptr(), stream))
+        if self.kind == "w8":
+            _lib.check(lib.cgq_decode_begin_w8(
+                self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
+                emb.weight.shape[0], emb.weight.shape[1], self.code, self.state.data_ptr(), stream))
+        else:
+            _lib.check(lib.cgq_decode_begin_w4(
+                self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
+                emb.weight.shape[0] * 2, emb.weight.shape[1], 32, self.code, self.state.data_ptr(), stream))
         firsts = [layer.attn.qkv_proj for layer in m.layers][1:] + [m.lm_head]
         if self.handover:
             self.ctr.zero_()

@@ -246,6 +246,29 @@ def gemv_fused_s4(a: Tensor, b: Tensor, b_scale: Tensor, bias: Tensor = None, re
     return out
 
 
+def gemv_fused_s8(a: Tensor, b: Tensor, b_scale: Tensor, bias: Tensor = None, resid: Tensor = None,
+                  prologue: int = _lib.PRO_NONE, norm_weight: Tensor = None, eps: float = 0.0,
+                  out: Tensor = None) -> Tensor:
+    """The int8 twin of `gemv_fused_s4` (cgq_w8a16_gemv_fused): `b` is the module's [N, K] int8 buffer itself
+    (int8/qlinear.py:82-87), `b_scale` its [N] per-channel scales."""
+    N, K = b.shape
+    code = _dtype_code(a)
+    assert a.dim() == 1 and a.is_contiguous() and a.numel() == (2 * K if prologue == _lib.PRO_SILU_GATE else K)
+    assert b.dtype == torch.int8 and b.is_contiguous() and b_scale.is_contiguous()
+    assert b_scale.shape == (N,) and b_scale.dtype == a.dtype
+    for t in (bias, resid):
+        assert t is None or (t.shape == (N,) and t.dtype == a.dtype and t.is_contiguous())
+    if prologue == _lib.PRO_RMSNORM:
+        assert norm_weight is not None and norm_weight.shape == (K,) and norm_weight.dtype == a.dtype
+    if out is None:
+        out = torch.empty(N, device=a.device, dtype=a.dtype)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().cgq_w8a16_gemv_fused(
+            a.data_ptr(), b.data_ptr(), b_scale.data_ptr(), _ptr(bias), _ptr(resid), out.data_ptr(), N, K, code, prologue,
+            _ptr(norm_weight), float(eps), torch.cuda.current_stream().cuda_stream))
+    return out
+
+
 def decode_attention(qkv: Tensor, freqs: Tensor, k_cache: Tensor, v_cache: Tensor, state: Tensor,
                      n_head: int, n_groups: int, d_head: int) -> Tensor:
     """ChatGLM2Attention.forward between qkv_proj and o_proj for one new token (cgq_decode_attention):

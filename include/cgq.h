@@ -303,6 +303,14 @@ int cgq_step_destroy(uint64_t handle);
 int cgq_decode_begin_w4(const int64_t* ids, const uint8_t* Wq /*[V/2, D]*/, const void* scale,
                         void* x, int V, int D, int group, int dtype, int* state, void* stream);
 
+/* The int8 twins of the fused decode step's entry points: per-channel int8 weights [N, K] (K contiguous) with
+ * scales [N] (int8/qlinear.py:77-107), int8 QEmbedding [V, D] with per-column scales [D] (int8/qlinear.py:110-132).  Same
+ * prologues / residual epilogue and roundings as the int4 versions; the per-channel scale multiplies the fp32 sum. */
+int cgq_w8a16_gemv_fused(const void* A, const int8_t* Wq, const void* scale, const void* bias, const void* resid,
+                         void* C, int N, int K, int dtype, int prologue, const void* norm_w, float eps, void* stream);
+int cgq_decode_begin_w8(const int64_t* ids, const int8_t* Wq /*[V, D]*/, const void* scale /*[D]*/, void* x, int V,
+                        int D, int dtype, int* state, void* stream);
+
 /*
  * ChatGLM2Attention.forward between qkv_proj and o_proj for one new token (model.py:140-174):
  * RoPE of q and k with row (state[1] + 1) of `freqs` (the model's freqs_cis_cache, [max_pos, d_head];

@@ -495,3 +495,103 @@ def test_step_program_rejects_what_it_cannot_take():
         prog.build()
     with pytest.raises(TypeError):
         ops.StepProgram(torch.bfloat16)
+
+
+# ------------------------------------------------------------------ int8 model through the fused step (BASELINE config 4)
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("k,n", [(4096, 4608), (4096, 4096), (13696, 4096), (4096, 27392), (512, 768), (6848, 4096), (1056, 144)])
+def test_gemv_fused_s8_vs_oracle(dtype, k, n):
+    """cgq_w8a16_gemv_fused (cluster / DSMEM int8 decode kernel): RMSNorm + bias, plain + residual in place,
+    SiLU-gate, on the real layer shapes (incl. K = 6848: a ragged last 128-k stage) against the numpy oracle; the
+    plain launch must equal the module-level op bit for bit."""
+    from util import make_int8_case
+
+    a, q, s = make_int8_case(61, 1, k, n, "Q", dtype)
+    rng = np.random.default_rng(k * 3 + n)
+    x = orc.round_to(a[0] * 2.0, dtype)
+    nw = orc.round_to(1.0 + 0.2 * rng.standard_normal(k), dtype)
+    bias = orc.round_to(rng.standard_normal(n) * 0.05, dtype)
+    resid = orc.round_to(rng.standard_normal(n), dtype)
+    W, S = torch.from_numpy(q).to(DEV), to_torch(s, dtype)
+    got = ops.gemv_fused_s8(to_torch(x, dtype), W, S, bias=to_torch(bias, dtype), prologue=PRO_RMSNORM,
+                            norm_weight=to_torch(nw, dtype), eps=1e-5)
+    want = orc.qmatmul_int8(dec.rmsnorm(x, nw, 1e-5, dtype)[None], q, s, bias, dtype)[0]
+    assert_parity(from_torch(got), want, f"int8 rmsnorm+linear {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+    xr = to_torch(resid, dtype)
+    got = ops.gemv_fused_s8(to_torch(x, dtype), W, S, resid=xr, out=xr)
+    want = orc.round_to(resid + orc.qmatmul_int8(x[None], q, s, None, dtype)[0], dtype)
+    assert_parity(from_torch(got), want, f"int8 linear+resid {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+    plain = ops.gemv_fused_s8(to_torch(x, dtype), W, S, bias=to_torch(bias, dtype))
+    mod = ops.dynamic_quant_matmul(to_torch(x, dtype)[None], W.t(), S, bias=to_torch(bias, dtype))
+    assert torch.equal(plain, mod[0])
+    u = orc.round_to(rng.standard_normal(2 * k) * 1.5, dtype)
+    got = ops.gemv_fused_s8(to_torch(u, dtype), W, S, prologue=PRO_SILU_GATE)
+    want = orc.qmatmul_int8(dec.silu_gate(u, dtype)[None], q, s, None, dtype)[0]
+    assert_parity(from_torch(got), want, f"int8 silu-gate+linear {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+
+
+def _random_ref_int8_model(cfg_kwargs, seed=4):
+    ref = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    from chatglm_q.int8.qlinear import DynamicQuantizeLinear, QEmbedding
+    from chatglm_q.loader import create_quant_int8_model
+    from chatglm_q.model import ChatGLM2Config
+
+    cfg = ChatGLM2Config(**cfg_kwargs)
+    with torch.device(DEV):
+        model = create_quant_int8_model(cfg, torch.float16)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, DynamicQuantizeLinear):
+                n, k = mod.out_features, mod.in_features
+                wq = torch.randint(-127, 128, (n, k), dtype=torch.int8, device=DEV, generator=g)
+                sc = (torch.rand(n, device=DEV, generator=g) * 0.5 + 0.75) / (73.0 * k ** 0.5)
+                b = (torch.randn(n, device=DEV, generator=g) * 0.05).half() if mod.bias is not None else None
+                mod.apply_weights_(wq, sc.half(), b)
+            elif isinstance(mod, QEmbedding):
+                mod.weight.copy_(torch.randint(-127, 128, mod.weight.shape, dtype=torch.int8, device=DEV, generator=g))
+                mod.weight_scale.copy_((torch.rand(mod.weight_scale.shape, device=DEV, generator=g) * 0.01 + 0.005).half())
+        for name, p in model.named_parameters():
+            if name.endswith("ln.weight"):
+                p.copy_((1.0 + 0.2 * torch.randn(p.shape, device=DEV, generator=g)).half())
+    return model.eval()
+
+
+@pytest.mark.parametrize("cfg_kwargs", [
+    dict(hidden_size=512, inner_hidden_size=1024, head_hidden_size=64, num_multi_query_groups=2, num_attention_heads=8,
+         num_layers=3, vocab_size=1024, max_sequence_length=256),
+    dict(hidden_size=4096, inner_hidden_size=13696, head_hidden_size=128, num_multi_query_groups=2,
+         num_attention_heads=32, num_layers=2, vocab_size=65024, max_sequence_length=512),   # ChatGLM2-6B layer shapes
+])
+def test_fused_decode_int8_matches_unmodified_reference_model(cfg_kwargs):
+    """The int8 model through the fused step, driven as ChatGLMDecoder.generate does, against the UNMODIFIED reference
+    int8 model (same kernels behind its QLinear modules) greedily."""
+    from chatglm_q_b200.install import install, uninstall
+
+    model = _random_ref_int8_model(cfg_kwargs)
+    install("chatglm_q")
+    try:
+        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
+        fused = accelerate(model, max_len=40)
+        assert isinstance(fused, FusedDecodeModel) and fused.kind == "w8"
+        with torch.no_grad():
+            _, lg_e, kv_e = model(input_ids=prompt)
+            _, lg_f, kv_f = fused(input_ids=prompt, past_key_values=None)
+            assert torch.equal(lg_e, lg_f)
+            tok = lg_e[0, -1].argmax().reshape(1, 1)
+            for step in range(24):
+                _, lg_e, kv_e = model(input_ids=tok, past_key_values=kv_e)
+                _, lg_f, kv_f = fused(input_ids=tok, past_key_values=kv_f)
+                a, b = lg_e[0, -1].float(), lg_f[0, -1].float()
+                assert torch.isfinite(b).all()
+                assert_parity(b.cpu().numpy(), a.cpu().numpy(), f"int8 step {step} logits", rtol=2e-2)
+                top2 = a.topk(2).values
+                if (top2[0] - top2[1]).item() > 2e-2 * a.abs().max().item():
+                    assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
+                tok = a.argmax().reshape(1, 1)
+    finally:
+        uninstall("chatglm_q")
