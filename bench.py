@@ -499,7 +499,9 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
     eager, eager_prefill, _ = run(ChatGLMDecoder(cfg, model, tok, device=device, time_log=False))
     graphed, graphed_prefill, _ = run(ChatGLMDecoder(cfg, GraphDecodeModel(model, max_len=prompt_len + gen_tokens + 32),
                                                      tok, device=device, time_log=False))
-    fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32)
+    # (alias_logits=True: ChatGLMDecoder.generate samples each step's logits at once, so the static logits row is
+    # handed out as is -- the default hands out a copy per step, as the reference returns a fresh tensor)
+    fused_model = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32, alias_logits=True)
     fused_ref_sampler, _, _ = run(ChatGLMDecoder(cfg, fused_model, tok, device=device, time_log=False))
     # the sampler is a module global of the reference too (decoder.py:12, resolved at :85): rebind it to the
     # one-launch cgq_top_p_sample (same signature, same token for the same seed) -- the headline configuration
@@ -565,6 +567,148 @@ def e2e_decode(torch, device, gen_tokens=128, prompt_len=32):
                                                  "(chatglm_q_b200.GraphDecodeModel), ~1100 kernels per token"},
             "eager": {"value": eager, "prefill_s": eager_prefill,
                       "how": "same decoder, model NOT wrapped: ~1100 eager kernels + torch.cat KV growth per token"}}
+
+
+# ----------------------------------------------------------------------------- BASELINE config 4: the int8 model
+def build_ref_int8_model(torch, device, seed=0):
+    """Random-init ChatGLM2-6B int8 model built by the reference's own factory (chatglm_q/loader.py:41-50)."""
+    from chatglm_q.loader import ChatGLMLoadConfig, create_quant_int8_model
+    from chatglm_q.model import ChatGLM2Config
+    from chatglm_q.int8.qlinear import DynamicQuantizeLinear, QEmbedding
+
+    cfg = ChatGLM2Config()
+    with torch.device(device):
+        model = create_quant_int8_model(cfg, torch.float16)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, DynamicQuantizeLinear):
+                n, k = mod.out_features, mod.in_features
+                wq = torch.randint(-127, 128, (n, k), dtype=torch.int8, device=device, generator=gen)
+                sc = (torch.rand(n, device=device, generator=gen) * 0.5 + 0.75) / (73.0 * k ** 0.5)
+                b = (torch.randn(n, device=device, generator=gen) * 0.02).half() if mod.bias is not None else None
+                mod.apply_weights_(wq, sc.half(), b)
+            elif isinstance(mod, QEmbedding):
+                mod.weight.copy_(torch.randint(-127, 128, mod.weight.shape, dtype=torch.int8, device=device, generator=gen))
+                mod.weight_scale.copy_((torch.rand(mod.weight_scale.shape, device=device, generator=gen) * 0.01 + 0.005).half())
+    model.eval()
+    return ChatGLMLoadConfig(model_config=cfg, quant_type="int8", torch_dtype="float16"), model
+
+
+def int8_config4(torch, device, peaks, gen_tokens=64, prompt_len=32):
+    """BASELINE.json configs[3]: ChatGLM2-6B int8 -- decode bs=1 (device chain of the 113 linears + e2e through the
+    unmodified decoder on the fused step), decode bs=8 (the 113 linears at M=8; `generate` is batch-1 only,
+    chatglm_q/decoder.py:70), prefill of 2 048 tokens through the unmodified forward (tcgen05 kernels)."""
+    from chatglm_q_b200 import ops
+
+    out = {}
+    gen = torch.Generator(device=device).manual_seed(11)
+    shapes = [("qkv", H, QKV_N, True), ("o", H, H, False), ("w_in", H, 2 * INNER, False), ("w_out", INNER, H, False)]
+
+    def w8(k, n, bias):
+        w = torch.randint(-127, 128, (n, k), dtype=torch.int8, device=device, generator=gen)
+        sc = ((torch.rand(n, device=device, generator=gen) * 0.5 + 0.75) / (73.0 * k ** 0.5)).half()
+        b = (torch.randn(n, device=device, generator=gen) * 0.02).half() if bias else None
+        return w, sc, b
+
+    layers = [[w8(k, n, b) for _, k, n, b in shapes] for _ in range(LAYERS)]
+    head = w8(H, VOCAB, False)
+    nbytes = lambda m: LAYERS * sum(k * n + 2 * n + 2 * m * k + 2 * m * n + (2 * n if b else 0) for _, k, n, b in shapes) \
+        + H * VOCAB + 2 * VOCAB + 2 * m * H + 2 * m * VOCAB  # noqa: E731
+    stream = torch.cuda.Stream(device=device)
+    for m in (1, 8):
+        x0 = torch.randn((m, H), device=device, generator=gen).half()
+
+        def chain():
+            x = x0
+            for (wq, sq, bq), (wo, so, _), (wi, si, _), (wu, su, _) in layers:
+                qkv = ops.dynamic_quant_matmul(x, wq.t(), sq, bias=bq)
+                o = ops.dynamic_quant_matmul(qkv[:, :H], wo.t(), so)
+                hin = ops.dynamic_quant_matmul(o, wi.t(), si)
+                x = ops.dynamic_quant_matmul(hin[:, :INNER], wu.t(), su)
+            return ops.dynamic_quant_matmul(x, head[0].t(), head[1])
+
+        with torch.cuda.stream(stream), torch.no_grad():
+            chain()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                lg = chain()
+            for _ in range(3):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(20):
+                g.replay()
+            e1.record(stream)
+            stream.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        assert torch.isfinite(lg.float()).all()
+        out[f"decode_bs{m}_linears"] = {"ms_per_step": round(ms, 4), "tok_s": round(m * 1e3 / ms, 1),
+                                        "GBps": round(nbytes(m) / ms / 1e6, 1),
+                                        "hbm_frac": round(nbytes(m) / ms / 1e6 / peaks["hbm_gbs"], 4),
+                                        "how": f"113 int8 dequant-matmuls at M={m} (cgq_w8a16_gemm), one CUDA graph"}
+        del g
+    del layers, head
+    torch.cuda.empty_cache()
+    if import_reference() is None:
+        return out
+    from chatglm_q.decoder import ChatGLMDecoder
+    import chatglm_q.decoder as decmod
+    from chatglm_q_b200.fused_decode import FusedDecodeModel
+    from chatglm_q_b200.install import install, uninstall
+
+    install("chatglm_q", sampler=True)
+    try:
+        cfg, model = build_ref_int8_model(torch, device)
+        fused = FusedDecodeModel(model, max_len=prompt_len + gen_tokens + 32, alias_logits=True)
+        times, real_perf = [], time.perf_counter
+
+        class _Clock:
+            @staticmethod
+            def perf_counter():
+                t = real_perf()
+                times.append(t)
+                return t
+
+            def __getattr__(self, k):
+                return getattr(time, k)
+
+        dec = ChatGLMDecoder(cfg, fused, StubTokenizer(prompt_len), device=device, time_log=False)
+        torch.manual_seed(0)
+        for _ in dec.generate("warm-up", max_generated_tokens=8):
+            pass
+        torch.cuda.synchronize()
+        decmod.time = _Clock()
+        try:
+            for _ in dec.generate("bench", max_generated_tokens=gen_tokens):
+                pass
+        finally:
+            decmod.time = time
+        steps = [b - a for a, b in zip(times[0::2], times[1::2])]
+        out["decode_bs1_e2e"] = {"tok_s": round(len(steps[1:]) / sum(steps[1:]), 2), "tokens": len(steps),
+                                 "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8,
+                                 "how": "unmodified ChatGLMDecoder.generate on FusedDecodeModel(int8 model): one CUDA-graph "
+                                        "replay of the fused step (cgq_w8a16_gemv_fused + attention) per token"}
+        # prefill of 2 048 tokens through the unmodified forward (its int8 QLinear modules run the tcgen05 kernels)
+        ids = torch.randint(1000, 60000, (1, 2048), generator=torch.Generator().manual_seed(0)).to(device)
+        with torch.no_grad():
+            fused(input_ids=ids, past_key_values=None)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                fused(input_ids=ids, past_key_values=None)
+            e1.record()
+            torch.cuda.synchronize()
+        out["prefill_2048"] = {"ms": round(e0.elapsed_time(e1) / 2, 2),
+                               "how": "2 048-token prompt through the unmodified reference forward, int8 tcgen05 kernels behind "
+                                      "its QLinear modules (eager glue of the reference included)"}
+        del model, fused
+    finally:
+        uninstall("chatglm_q")
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -769,6 +913,8 @@ def run_own_arm(args):
                        {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "--no-e2e"})
         if not args.no_micro:
             line["microbench"] = microbench(torch, device, peaks)
+        if not args.no_int8:
+            line["int8"] = int8_config4(torch, device, peaks)
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             cstep, kind = cpu_reference_step(threads)
@@ -934,6 +1080,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-int8", action="store_true", help="skip the int8 model (BASELINE configs[3]) sub-dict")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == "reference" else 500

@@ -3,7 +3,7 @@
 # and the 142-launch fused step through tools/chainbench), full captures of the decode / attention kernels.
 # Usage (under gpurun): bash scripts/gpu_profile.sh <tag>
 tag=${1:-prof}; out=gpurun_out/$tag; mkdir -p $out
-B="python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-micro --no-cpu"
+B="python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-micro --no-cpu --no-int8"
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
 timeout 900 ncu --metrics $M --clock-control none -k regex:w4_gemv -s 565 -c 113 --csv \
   --log-file $out/launches_token.csv $B > $out/ncu_launch.log 2>&1

@@ -2,7 +2,7 @@
 # round-end ncu evidence for the CURRENT build: launch list of one token step of the bench `value` (113 launches),
 # full captures of the decode kernel inside the fused step and of the sampler kernel
 tag=${1:-prof}; out=gpurun_out/$tag; mkdir -p $out
-B="python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-micro --no-cpu"
+B="python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-micro --no-cpu --no-int8"
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
 timeout 400 ncu --metrics $M --clock-control none -k regex:w4_gemv -s 565 -c 113 --csv \
   --log-file $out/launches_token.csv $B > $out/ncu_launch.log 2>&1
