@@ -37,6 +37,10 @@ SYMBOLS = {
     "cgq_step_run": (c_int, [ctypes.c_uint64, c_void_p]),
     "cgq_step_status": (c_int, [ctypes.c_uint64, c_void_p, c_void_p, c_void_p]),
     "cgq_step_destroy": (c_int, [ctypes.c_uint64]),
+    "cgq_w4a16_grad_a": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
+    "cgq_w8a16_grad_a": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
     "cgq_tp_next": (c_int, [c_void_p, ctypes.c_uint32]),
     "cgq_tp_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cgq_ipc_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),

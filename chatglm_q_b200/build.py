@@ -14,7 +14,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libcgq.so"
-SOURCES = ["cabi.cu", "simple_kernels.cu", "gemv_w4.cu", "gemv_w4_umma.cu", "gemv_w8.cu", "gemm_tc.cu", "decode_step.cu", "decode_program.cu", "decode_mk.cu", "tp_ipc.cu", "sampling.cu"]
+SOURCES = ["cabi.cu", "simple_kernels.cu", "gemv_w4.cu", "gemv_w4_umma.cu", "gemv_w8.cu", "gemm_tc.cu", "decode_step.cu", "decode_program.cu", "decode_mk.cu", "tp_ipc.cu", "backward.cu", "sampling.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -26,15 +26,19 @@ def install(package: str = "chatglm_q", sampler=False) -> None:
     (`ops._delegates`), so a configuration that works in the reference keeps working after install()."""
     q4 = importlib.import_module(f"{package}.int4.qlinear")
     q8 = importlib.import_module(f"{package}.int8.qlinear")
-    for mod, impl, slot in ((q4, ops.dynamic_quant_matmul_s4, "s4"), (q8, ops.dynamic_quant_matmul, "s8")):
+    for mod, impl, impl_t, slot in ((q4, ops.dynamic_quant_matmul_s4, ops.dynamic_quant_matmul_transposed_s4, "s4"),
+                                    (q8, ops.dynamic_quant_matmul, ops.dynamic_quant_matmul_transposed, "s8")):
         if mod.__name__ not in _saved:
             _saved[mod.__name__] = {
                 k: getattr(mod, k, None)
-                for k in ("_dynamic_quant_matmul_impl", "check_input", "KERNEL_IMPL")
+                for k in ("_dynamic_quant_matmul_impl", "_dynamic_quant_matmul_transposed_impl", "check_input", "KERNEL_IMPL")
             }
         orig = _saved[mod.__name__]["_dynamic_quant_matmul_impl"]
+        orig_t = _saved[mod.__name__]["_dynamic_quant_matmul_transposed_impl"]
         ops._delegates[slot] = orig if callable(orig) else None
+        ops._delegates[slot + "t"] = orig_t if callable(orig_t) else None
         mod._dynamic_quant_matmul_impl = impl
+        mod._dynamic_quant_matmul_transposed_impl = impl_t      # DynamicQuantizeMatMul.backward (int4/qlinear.py:53-64)
         mod.check_input = ops.check_input
         mod.KERNEL_IMPL = "cgq_b200"
     if sampler:
@@ -47,7 +51,7 @@ def install(package: str = "chatglm_q", sampler=False) -> None:
 
 
 def uninstall(package: str = "chatglm_q") -> None:
-    ops._delegates.update({"s4": None, "s8": None, "sampler": None})
+    ops._delegates.update({"s4": None, "s8": None, "s4t": None, "s8t": None, "sampler": None})
     for name in (f"{package}.int4.qlinear", f"{package}.int8.qlinear", f"{package}.decoder"):
         saved = _saved.pop(name, None)
         if saved is None:

@@ -21,7 +21,7 @@ _ws_bytes = None
 # rebind.  Configurations this library does not build -- fp32 activations, group sizes other than 32, CPU / fp32
 # logits or top_k > 1024 in the sampler -- are handed to them unchanged, so that install() never turns a call that
 # works in the reference into an error.  Not a fallback of this library's own: without install() those inputs raise.
-_delegates: dict[str, object] = {"s4": None, "s8": None, "sampler": None}
+_delegates: dict[str, object] = {"s4": None, "s8": None, "s4t": None, "s8t": None, "sampler": None}
 
 
 def check_input(a: Tensor) -> bool:
@@ -158,6 +158,57 @@ def dynamic_quant_matmul(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool
         _lib.check(lib.cgq_w8a16_gemm_ex(
             a.data_ptr(), a.stride(0) if M > 1 else K, w_nk.data_ptr(), b_scale.data_ptr(),
             _ptr(bias), c.data_ptr(), N, M, N, K, code, ws.data_ptr(), ws.numel(), stream, impl))
+    return c.reshape(output_shape)
+
+
+def dynamic_quant_matmul_transposed_s4(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool = None) -> Tensor:
+    """Backward of `dynamic_quant_matmul_s4` with respect to its activation: a = grad_out (..., N), b uint8 (K//2, N),
+    b_scale (K//32, N) -> grad_A (..., K) = a @ unpack_int4(b, b_scale).T.  Drop-in for
+    chatglm_q.int4.triton_ops.dynamic_quant_matmul_transposed_s4 (int4/triton_ops.py:208-264) without its power-of-two
+    restrictions; `DynamicQuantizeMatMul.backward` calls it (int4/qlinear.py:53-64)."""
+    K = b.shape[0] * 2
+    output_shape = (*a.shape[:-1], K)
+    a = a.flatten(0, -2)
+    assert len(b.shape) == 2 and len(b_scale.shape) == 2
+    assert a.shape[1] == b.shape[1] and b.shape[1] == b_scale.shape[1]
+    assert b.dtype == torch.uint8 and a.dtype == b_scale.dtype
+    assert a.get_device() >= 0 and b.get_device() == a.get_device() and b_scale.get_device() == a.get_device()
+    M, N = a.shape
+    group = K // b_scale.shape[0]
+    if (group != 32 or a.dtype not in _DTYPE_CODE) and _delegates["s4t"] is not None:
+        return _delegates["s4t"](a.reshape(*output_shape[:-1], N), b, b_scale, allow_tf32)
+    assert group == 32, f"only the reference model's group size 32 is built, got {group}"
+    code = _dtype_code(a)
+    a, b, b_scale = a.contiguous(), b.contiguous(), b_scale.contiguous()
+    c = torch.empty((M, K), device=a.device, dtype=a.dtype)
+    if M:
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().cgq_w4a16_grad_a(a.data_ptr(), N, b.data_ptr(), b_scale.data_ptr(), c.data_ptr(), K, M, N,
+                                                    K, group, code, torch.cuda.current_stream().cuda_stream))
+    return c.reshape(output_shape)
+
+
+def dynamic_quant_matmul_transposed(a: Tensor, b: Tensor, b_scale: Tensor, allow_tf32: bool = None) -> Tensor:
+    """int8 twin (int8/triton_ops.py:196-245, `DynamicQuantizeMatMul.backward` int8/qlinear.py:41-52): a = grad_out
+    (..., N), b the (K, N) transposed VIEW of the module's [N, K] int8 buffer, b_scale (N,) -> grad_A (..., K)."""
+    K, N = b.shape
+    output_shape = (*a.shape[:-1], K)
+    a = a.flatten(0, -2)
+    assert a.shape[1] == N and b_scale.shape == (N,) and b.dtype == torch.int8 and a.dtype == b_scale.dtype
+    assert a.get_device() >= 0 and b.get_device() == a.get_device() and b_scale.get_device() == a.get_device()
+    if a.dtype not in _DTYPE_CODE and _delegates["s8t"] is not None:
+        return _delegates["s8t"](a.reshape(*output_shape[:-1], N), b, b_scale, allow_tf32)
+    code = _dtype_code(a)
+    w_nk = b.t()
+    if not w_nk.is_contiguous():
+        w_nk = w_nk.contiguous()
+    a, b_scale = a.contiguous(), b_scale.contiguous()
+    M = a.shape[0]
+    c = torch.empty((M, K), device=a.device, dtype=a.dtype)
+    if M:
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().cgq_w8a16_grad_a(a.data_ptr(), N, w_nk.data_ptr(), b_scale.data_ptr(), c.data_ptr(), K, M,
+                                                    N, K, code, torch.cuda.current_stream().cuda_stream))
     return c.reshape(output_shape)
 
 

@@ -10,7 +10,8 @@ What the reference loader and model rely on, and what is therefore kept identica
     int8/qlinear.py:82-87), so `state_dict()` keys and the loader's by-key `copy_` still work;
   * `apply_weights_` as used by the quantiser scripts.
 Forward runs on the sm_100a kernels with the bias add fused (same two roundings as the
-reference's separate `out += bias`).  Inference only — no autograd is registered.
+reference's separate `out += bias`).  `dynamic_quant_matmul_int4/8` are differentiable in the activation
+(grad_A on `cgq_w4a16_grad_a` / `cgq_w8a16_grad_a`); the Linear modules' fused-bias forward is inference-only.
 """
 from __future__ import annotations
 
@@ -126,19 +127,45 @@ class W8Embedding(_QuantModule):
         return ops.embedding_s8(input, self.weight, self.weight_scale)
 
 
-def _no_grad_guard(A: Tensor) -> None:
-    if A.requires_grad and torch.is_grad_enabled():
-        raise RuntimeError("chatglm_q_b200: the dequant-matmul path is inference-only (no backward; "
-                           "reference backward = int4/qlinear.py:53-64, out of scope)")
+class _QMatMulS4(torch.autograd.Function):
+    """`DynamicQuantizeMatMul` of the int4 model (int4/qlinear.py:36-64): forward and grad_A on this repo's kernels."""
+
+    @staticmethod
+    def forward(ctx, A: Tensor, B: Tensor, b_scale: Tensor):
+        ctx.save_for_backward(B, b_scale)
+        return ops.dynamic_quant_matmul_s4(A, B, b_scale)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        B, b_scale = ctx.saved_tensors
+        grad_A = ops.dynamic_quant_matmul_transposed_s4(grad_out, B, b_scale) if ctx.needs_input_grad[0] else None
+        return grad_A, None, None
+
+
+class _QMatMulS8(torch.autograd.Function):
+    """`DynamicQuantizeMatMul` of the int8 model (int8/qlinear.py:24-52)."""
+
+    @staticmethod
+    def forward(ctx, A: Tensor, B: Tensor, b_scale: Tensor):
+        ctx.save_for_backward(B, b_scale)
+        return ops.dynamic_quant_matmul(A, B, b_scale)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        B, b_scale = ctx.saved_tensors
+        grad_A = ops.dynamic_quant_matmul_transposed(grad_out, B, b_scale) if ctx.needs_input_grad[0] else None
+        return grad_A, None, None
 
 
 def dynamic_quant_matmul_int4(A: Tensor, B: Tensor, b_scale: Tensor) -> Tensor:
-    """chatglm_q.int4.qlinear.dynamic_quant_matmul (int4/qlinear.py:71-72), forward only."""
-    _no_grad_guard(A)
+    """chatglm_q.int4.qlinear.dynamic_quant_matmul (int4/qlinear.py:71-72): differentiable in A."""
+    if A.requires_grad and torch.is_grad_enabled():
+        return _QMatMulS4.apply(A, B, b_scale)
     return ops.dynamic_quant_matmul_s4(A, B, b_scale)
 
 
 def dynamic_quant_matmul_int8(A: Tensor, B: Tensor, b_scale: Tensor) -> Tensor:
-    """chatglm_q.int8.qlinear.dynamic_quant_matmul (int8/qlinear.py:73-74), forward only."""
-    _no_grad_guard(A)
+    """chatglm_q.int8.qlinear.dynamic_quant_matmul (int8/qlinear.py:73-74): differentiable in A."""
+    if A.requires_grad and torch.is_grad_enabled():
+        return _QMatMulS8.apply(A, B, b_scale)
     return ops.dynamic_quant_matmul(A, B, b_scale)

@@ -208,6 +208,19 @@ int cgq_program_status(uint64_t handle, int* workers, int* failed);
 int cgq_program_destroy(uint64_t handle);
 
 /*
+ * ---- Backward with respect to the activation ----------------------------------------------
+ * grad_A[M, K] = grad_out[M, N] . dequant(W)^T -- `DynamicQuantizeMatMul.backward` (int4/qlinear.py:53-64,
+ * int8/qlinear.py:41-52; Triton twins int4/triton_ops.py:142-264, int8/triton_ops.py:130-245).  Weight layouts as in
+ * the forward entry points (int4: Wq [K/2, N] + scale [K/32, N]; int8: Wq [N, K] + scale [N]).  Every element is
+ * dequantised with the reference's single rounding, fp32 accumulation, one final rounding.  CUDA-core kernel, any
+ * shape (the reference's Triton kernel needs power-of-two sizes).
+ */
+int cgq_w4a16_grad_a(const void* grad_out, int64_t ldg, const uint8_t* Wq, const void* scale, void* grad_a, int64_t ldo,
+                     int M, int N, int K, int group, int dtype, void* stream);
+int cgq_w8a16_grad_a(const void* grad_out, int64_t ldg, const int8_t* Wq, const void* scale, void* grad_a, int64_t ldo,
+                     int M, int N, int K, int dtype, void* stream);
+
+/*
  * ---- Tensor parallelism of the fused decode step (no reference counterpart: the reference is single-GPU) ------
  * One process per GPU.  Column-parallel linears (qkv_proj, w_in, lm_head) need no exchange; a ROW-parallel linear
  * (o_proj, w_out: this rank holds a k-slice) exchanges its fp32 partial sums INSIDE the decode kernel's epilogue:

@@ -137,6 +137,25 @@ def qmatmul_int8(a: np.ndarray, w_nk: np.ndarray, w_scale: np.ndarray, bias: np.
     return out.reshape(*lead, w.shape[1])
 
 
+def qmatmul_int4_grad_a(grad_out: np.ndarray, b: np.ndarray, b_scale: np.ndarray, dtype: str = "float16") -> np.ndarray:
+    """`DynamicQuantizeMatMul.backward` of the int4 model on its torch path:
+    `grad_A = grad_out.matmul(unpack_int4(B, b_scale).t())` (int4/qlinear.py:53-64).
+    Dequantised weight rounded once per element, fp32 accumulation, one final rounding."""
+    w = unpack_int4(b, b_scale, dtype)
+    lead = grad_out.shape[:-1]
+    g2 = np.asarray(grad_out, dtype=np.float32).reshape(-1, grad_out.shape[-1])
+    return round_to(g2 @ w.T, dtype).reshape(*lead, w.shape[0])
+
+
+def qmatmul_int8_grad_a(grad_out: np.ndarray, w_nk: np.ndarray, w_scale: np.ndarray, dtype: str = "float16") -> np.ndarray:
+    """int8 twin: `grad_A = grad_out.matmul((B * b_scale).t())` with B = weight.t() (int8/qlinear.py:41-52)."""
+    assert w_nk.dtype == np.int8 and w_nk.ndim == 2
+    w = round_to(w_nk.T.astype(np.float32) * np.asarray(w_scale, dtype=np.float32)[None, :], dtype)
+    lead = grad_out.shape[:-1]
+    g2 = np.asarray(grad_out, dtype=np.float32).reshape(-1, grad_out.shape[-1])
+    return round_to(g2 @ w.T, dtype).reshape(*lead, w.shape[0])
+
+
 def quantize_int8(x: np.ndarray):
     """Per-row abs-max / 127 symmetric int8.  Reference: chatglm_q/int8/quantizer.py:11-19
     (x is the [N, K] (out_dim, in_dim) weight)."""

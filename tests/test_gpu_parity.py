@@ -344,8 +344,64 @@ def test_module_forward_matches_oracle():
     with torch.no_grad():
         y8 = lin8(to_torch(a8, "float16"))
     assert_parity(from_torch(y8), c_oracle.w8a16_gemm(a8, q8, s8, None, "float16"), "W8Linear")
-    with pytest.raises(RuntimeError):  # inference only
-        m4.dynamic_quant_matmul(to_torch(a, "float16").requires_grad_(), u8(bq), to_torch(s, "float16"))
+    # differentiable in the activation (DynamicQuantizeMatMul.backward, int4/qlinear.py:53-64)
+    at = to_torch(a, "float16").requires_grad_()
+    go = orc.round_to(np.random.default_rng(3).standard_normal((m, n)) * 0.1, "float16")
+    m4.dynamic_quant_matmul(at, u8(bq), to_torch(s, "float16")).backward(to_torch(go, "float16"))
+    assert_parity(from_torch(at.grad), orc.qmatmul_int4_grad_a(go, bq, s, "float16"), "int4 autograd grad_A")
+
+
+# ------------------------------------------------------------------ backward
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_grad_a_matches_oracle_and_reference_golden(dtype):
+    """cgq_w4a16_grad_a / cgq_w8a16_grad_a against the oracle on the golden inputs of the real reference's autograd
+    (tests/golden/backward.npz) and on shapes the reference's Triton backward cannot take (N = 13696: not a power of
+    two, int4/triton_ops.py:226-229)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "backward.npz")
+    for tag in ("a", "b"):
+        go = orc.round_to(g[f"s4_{tag}_grad_out"], dtype)
+        sc = orc.round_to(g[f"s4_{tag}_scale"], dtype)
+        got = ops.dynamic_quant_matmul_transposed_s4(to_torch(go, dtype), u8(g[f"s4_{tag}_b"]), to_torch(sc, dtype))
+        assert_parity(from_torch(got), orc.qmatmul_int4_grad_a(go, g[f"s4_{tag}_b"], sc, dtype), f"int4 grad_A {tag}", rtol=rtol_for(dtype))
+        if dtype == "float16":   # fp32 golden of the reference itself, fp16 rounding of inputs / output inside the bar
+            assert_parity(from_torch(got), g[f"s4_{tag}_grad_a"], f"int4 grad_A {tag} vs reference fp32", rtol=2e-2)
+        s8 = orc.round_to(g[f"s8_{tag}_scale"], dtype)
+        w = torch.from_numpy(g[f"s8_{tag}_w"]).to(DEV)
+        got = ops.dynamic_quant_matmul_transposed(to_torch(go, dtype), w.t(), to_torch(s8, dtype))
+        assert_parity(from_torch(got), orc.qmatmul_int8_grad_a(go, g[f"s8_{tag}_w"], s8, dtype), f"int8 grad_A {tag}", rtol=rtol_for(dtype))
+    # a real layer shape with leading dims: w_out of ChatGLM2-6B seen from its output side
+    k, n, m = 13696, 4096, 6
+    a, bq, s = make_int4_case(31, m, k, n, "Q", dtype)
+    go = orc.round_to(np.random.default_rng(5).standard_normal((2, 3, n)) * 0.05, dtype)
+    got = ops.dynamic_quant_matmul_transposed_s4(to_torch(go, dtype), u8(bq), to_torch(s, dtype))
+    assert got.shape == (2, 3, k)
+    assert_parity(from_torch(got), orc.qmatmul_int4_grad_a(go, bq, s, dtype), "int4 grad_A w_out", rtol=rtol_for(dtype))
+    empty = ops.dynamic_quant_matmul_transposed_s4(to_torch(go[:0], dtype), u8(bq), to_torch(s, dtype))
+    assert empty.shape == (0, 3, k)
+
+
+def test_install_routes_reference_backward():
+    """After install() the unmodified reference `DynamicQuantizeMatMul.backward` (int4/qlinear.py:53-64) runs on
+    cgq_w4a16_grad_a, also for shapes its own Triton backward asserts on."""
+    import sys
+    from pathlib import Path
+    ref = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
+    if not (ref / "chatglm_q").exists():
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    sys.path.insert(0, str(ref))
+    import chatglm_q_b200
+    from chatglm_q.int4 import qlinear as rq4
+    chatglm_q_b200.install("chatglm_q")
+    try:
+        k, n, m = 256, 208, 4
+        a, bq, s = make_int4_case(41, m, k, n, "Q")
+        at = to_torch(a, "float16").requires_grad_()
+        go = orc.round_to(np.random.default_rng(6).standard_normal((m, n)) * 0.1, "float16")
+        rq4.dynamic_quant_matmul(at, u8(bq), to_torch(s, "float16")).backward(to_torch(go, "float16"))
+        assert_parity(from_torch(at.grad), orc.qmatmul_int4_grad_a(go, bq, s, "float16"), "reference autograd on cgq")
+    finally:
+        chatglm_q_b200.uninstall("chatglm_q")
 
 
 # ------------------------------------------------------------------ graph-captured decode step (SURVEY §8f.1)

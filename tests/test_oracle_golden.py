@@ -112,6 +112,19 @@ def test_qembedding(golden):
     assert np.array_equal(got8, golden["e8_y"].astype(np.float32))
 
 
+def test_backward_grad_a_matches_reference_autograd():
+    """grad_A oracles against autograd through the real reference's torch path (tests/golden/make_golden_backward.py);
+    fp32, the reference tests' own 1e-4 criterion (tests/test_triton_ops_int4.py:24-37)."""
+    g = np.load(ROOT / "tests" / "golden" / "backward.npz")
+    for tag in ("a", "b"):
+        got = orc.qmatmul_int4_grad_a(g[f"s4_{tag}_grad_out"], g[f"s4_{tag}_b"], g[f"s4_{tag}_scale"], "float32")
+        want = g[f"s4_{tag}_grad_a"]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+        got = orc.qmatmul_int8_grad_a(g[f"s4_{tag}_grad_out"], g[f"s8_{tag}_w"], g[f"s8_{tag}_scale"], "float32")
+        want = g[f"s8_{tag}_grad_a"]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+
+
 def test_config1_int8_plumbing():
     """BASELINE.json configs[0]: int8 QLinear forward (128,4096)x(4096,4096) on the CPU path."""
     fx = dict(np.load(ROOT / "tests" / "golden" / "config1_int8.npz"))

@@ -21,7 +21,14 @@ __global__ void mma_loop(int iters, unsigned long long* out, float* sink) {
             "{%0,%1,%2,%3};"
             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3])
             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-      else
+      else if (KIND == 2) {
+        int* di = reinterpret_cast<int*>(d[c]);
+        asm volatile(
+            "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+            "{%0,%1,%2,%3};"
+            : "+r"(di[0]), "+r"(di[1]), "+r"(di[2]), "+r"(di[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      } else
         asm volatile(
             "mma.sync.aligned.m16n8k32.row.col.f32.e4m3.e4m3.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
             "{%0,%1,%2,%3};"
@@ -74,6 +81,11 @@ int main() {
   run<1, 8>("QMMA.16832.e4m3", 8);
   run<1, 8>("QMMA.16832.e4m3", 16);
   run<1, 1>("QMMA.16832.e4m3 (dependent chain)", 4);
+  run<2, 8>("IMMA.16832.u8.s8", 4);
+  run<2, 8>("IMMA.16832.u8.s8", 8);
+  run<2, 8>("IMMA.16832.u8.s8", 16);
+  run<2, 4>("IMMA.16832.u8.s8 (4 chains)", 4);
+  run<2, 1>("IMMA.16832.u8.s8 (dependent chain)", 4);
   uint32_t* d;
   cudaMalloc(&d, 64 * 4);
   ldsm_probe<<<1, 32>>>(d);
