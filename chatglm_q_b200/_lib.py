@@ -22,6 +22,7 @@ SYMBOLS = {
     "cgq_w8a16_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int]),
     "cgq_debug_trace": (None, [c_void_p]),
+    "cgq_set_decode_arith": (c_int, [c_int]),
     "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),
     "cgq_w8a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -63,6 +64,8 @@ SYMBOLS = {
 }
 
 IMPL_AUTO, IMPL_SIMPLE, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_TC, IMPL_GEMV_UMMA = 0, 1, 2, 3, 4, 5
+IMPL_GEMV_SUBNORMAL, IMPL_GEMV_IMMA = 6, 7
+ARITH_IMMA, ARITH_EXACT, ARITH_SUBNORMAL = 0, 1, 2      # cgq_set_decode_arith
 PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE = 0, 1, 2
 
 _lib = None

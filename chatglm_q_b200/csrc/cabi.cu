@@ -183,6 +183,7 @@ extern "C" int cgq_version(void) { return (0 << 16) | 2; }
 extern "C" const char* cgq_last_error(void) { return g_err; }
 extern "C" size_t cgq_workspace_bytes(void) { return kWorkspaceBytes; }
 extern "C" void cgq_debug_trace(void* device_buffer) { g_trace = device_buffer; }
+extern "C" int cgq_set_decode_arith(int arith) { return default_w4_arith(arith); }
 
 extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, const void* scale,
                                  const void* bias, void* C, int64_t ldc, int M, int N, int K,
@@ -234,13 +235,18 @@ extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, 
       return launch_w4_tc(a);
     case CGQ_IMPL_GEMV:
     case CGQ_IMPL_GEMV_EXACT:
+    case CGQ_IMPL_GEMV_SUBNORMAL:
+    case CGQ_IMPL_GEMV_IMMA:
       if (M > 8 || !w4_gemv_supported(a)) {
         set_error("%s: GEMV kernel needs M<=8, N%%16==0, 16-byte aligned pointers, lda%%8==0", fn);
         return CGQ_ERR_MISALIGNED;
       }
       rc = check_workspace(fn, workspace, workspace_bytes);
       if (rc != CGQ_OK) return rc;
-      return launch_w4_gemv(a, impl == CGQ_IMPL_GEMV_EXACT);
+      return launch_w4_gemv(a, impl == CGQ_IMPL_GEMV_EXACT       ? W4_ARITH_EXACT
+                               : impl == CGQ_IMPL_GEMV_SUBNORMAL ? W4_ARITH_SUBNORMAL
+                               : impl == CGQ_IMPL_GEMV_IMMA      ? W4_ARITH_IMMA
+                                                                 : W4_ARITH_DEFAULT);
     default:
       set_error("%s: unknown impl %d", fn, impl);
       return CGQ_ERR_BAD_SHAPE;

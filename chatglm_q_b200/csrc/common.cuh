@@ -106,7 +106,12 @@ void set_w4_handover(const unsigned* wait_ctr, unsigned wait_count, unsigned* si
 void set_w4_tp(const cgq_tp_ctx& ctx, unsigned idx);
 int w4_gemv_tiles(int N);
 int launch_w8_simple(const GemmArgs& a);
-int launch_w4_gemv(const GemmArgs& a, bool exact);
+// arithmetic of the int4 decode kernel (gemv_w4.cu).  DEFAULT = CGQ_GEMV_ARITH (0 = IMMA unless set): integer MMA on
+// base-128 digits of the activation at M == 1, the subnormal-operand f16 MMA at M > 1; EXACT = (q - 8) converted
+// exactly to T, f16 / bf16 MMA; SUBNORMAL = fp16 nibbles as subnormal operands at every M (round-1/2 kernel).
+enum { W4_ARITH_DEFAULT = -1, W4_ARITH_IMMA = 0, W4_ARITH_EXACT = 1, W4_ARITH_SUBNORMAL = 2 };
+int launch_w4_gemv(const GemmArgs& a, int arith);
+int default_w4_arith(int set);
 int launch_w4_gemv_umma(const GemmArgs& a, bool* taken);
 int launch_w8_gemv(const GemmArgs& a);
 int launch_w8_gemv_fused(const GemmArgs& a, const GemvFused& fu);

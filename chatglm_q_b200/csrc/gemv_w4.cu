@@ -38,6 +38,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -46,6 +47,7 @@
 #include "w4_dev.cuh"
 
 namespace cgq {
+int default_w4_arith(int set);
 namespace {
 
 using namespace w4;
@@ -234,7 +236,7 @@ __device__ __forceinline__ void store_column(const Params& p, float acc, int n, 
   }
 }
 
-template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
+template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false, bool kImma = false>
 __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     w4_gemv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmS,
                    const Params p) {
@@ -332,8 +334,13 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     const int tid = threadIdx.x;                 // 0 .. CW*32-1
     const int nchunk = p.K >> 3;                 // valid chunks of the activation row
     const int c_lo = u0 * (KSTAGE / 8), c_hi = u1 * (KSTAGE / 8);
+    const uint32_t dig_info = Aband + p.band_units * DIG_STAGE;   // kImma: per-group 2^-shift behind the digits
     auto put = [&](int c, bool inband, const uint4& v) {
-      if (inband) ptx::sts128(Aband + (c - c_lo) * 16, v);
+      if constexpr (kImma) {
+        put_digits<T>(Aband, dig_info, c - c_lo, inband, v);
+      } else {
+        if (inband) ptx::sts128(Aband + (c - c_lo) * 16, v);
+      }
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
     if (kPro == PRO_RMSNORM) {
@@ -407,8 +414,88 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     for (int i = 0; i < NT; ++i) tot[j][i] = 0.f;
 
   int slot = 0, phase = 0;
-  constexpr bool kLdsm = kM1 && kTrick;   // fp16, one token: unpack through ldmatrix, see below
-  if constexpr (kLdsm) {
+  constexpr bool kLdsm = kM1 && kTrick && !kImma;   // fp16, one token: unpack through ldmatrix, see below
+  if constexpr (kImma) {
+    // One token on the INTEGER tensor pipe.  The packed bytes are the A operand almost as they
+    // are: ldmatrix.m16n16.trans.b8 hands lane (g, tig) the bytes of packed rows 4 tig .. 4 tig + 3 of columns
+    // 16 jj + g and 16 jj + g + 8, i.e. one 32-bit A-fragment register of IMMA.16832 per output column, and
+    // `word & 0x0F0F0F0F` / `word & 0xF0F0F0F0` are its even-k nibbles q and its odd-k nibbles as 16 q: TWO
+    // integer-pipe instructions per 8 weights (the f16 path needs five) and one MMA per 512 (f16: 256).
+    // The activation enters as four signed base-128 digits per element (put_digits) in MMA columns 0-3 / 4-7:
+    // the MMA of an even jj carries them in columns 0-3, the MMA of jj + 1 in columns 4-7 and accumulates onto the
+    // first one's result, so all 32 lanes own live accumulators (lane tig: digits 2 (tig & 1), + 1 of column block
+    // jj = 2 c + (tig >> 1)).  The accumulator starts from kMagicI - 8 (sum_even d + 16 sum_odd d), the -8 offset
+    // of the nibbles, produced by one extra MMA against constant (-8, -128) rows: the s32 result IS the fp32
+    // number 1.5 2^23 + sum, one FADD away from the exact integer group sum -- no I2F on the quarter-rate pipe.
+    const int P = tig >> 1;
+    const float wa = (tig & 1) ? 128.f : 2097152.f, wb = (tig & 1) ? 1.f : 16384.f;   // weights of this lane's digits
+    const uint32_t m0 = g < 4 ? 0xFFFFFFFFu : 0u;                  // this lane's B column is a digit of block P = 0 / 1
+    const int lrow = 16 * warp + (lane & 15);
+    uint32_t ld_off[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      ld_off[c] = static_cast<uint32_t>(lrow * BN + (((2 * c + (lane >> 4)) ^ (lrow & 7)) << 4));
+    // scale rows through one ldmatrix.x4.trans.b16: matrix c, row r <-> 16-byte chunk 4 c + 2 (r >> 2) + (r & 1)
+    const uint32_t sc_off = static_cast<uint32_t>(warp * (BN * 2) + (4 * (lane >> 3) + 2 * ((lane & 7) >> 2) + (lane & 1)) * 16);
+    const uint32_t dig_off = Aband + warp * 128 + (g & 3) * 32 + tig * 8;
+    const uint32_t info_off = Aband + p.band_units * DIG_STAGE + warp * 4;
+    float ti[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ti[c][0] = ti[c][1] = 0.f;
+    for (int it = 0; it < n_units; ++it) {
+      const uint2 bv = ptx::lds64(dig_off + it * DIG_STAGE);
+      const float inv = __uint_as_float(ptx::lds32(info_off + it * DIG_INFO));
+      const uint32_t neg[4] = {0xF8F8F8F8u, 0xF8F8F8F8u, 0x80808080u, 0x80808080u};   // -8 (even k), -128 (odd k / 16)
+      const int magic[4] = {kMagicI, kMagicI, kMagicI, kMagicI};
+      int off[4];
+      ptx::imma_s8s8(off, neg, bv.x, bv.y, magic);
+      const uint32_t b0a = bv.x & m0, b1a = bv.y & m0, b0b = bv.x & ~m0, b1b = bv.y & ~m0;
+      ptx::mbar_wait(&full[slot], phase);
+      if (it == 0 && threadIdx.x == 0) stamp(p, 3);
+      const uint32_t wrow = Wsm + slot * W_BYTES;
+      int d[4][4];
+      uint32_t dep = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[4];
+        ptx::ldsm_x2_trans_b8(wrow + ld_off[c], r);
+        dep |= r[0];
+        const uint32_t a0[4] = {r[0] & 0x0F0F0F0Fu, r[1] & 0x0F0F0F0Fu, r[0] & 0xF0F0F0F0u, r[1] & 0xF0F0F0F0u};
+        const uint32_t a1[4] = {r[2] & 0x0F0F0F0Fu, r[3] & 0x0F0F0F0Fu, r[2] & 0xF0F0F0F0u, r[3] & 0xF0F0F0F0u};
+        ptx::imma_u8s8(d[c], a0, b0a, b1a, off);
+        ptx::imma_u8s8(d[c], a1, b0b, b1b, d[c]);
+      }
+      uint32_t sw[4];
+      ptx::ldsm_x4_trans_b16(Ssm + slot * S_BYTES + sc_off, sw);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_after_loads(&empty[slot], dep | sw[3], rt_zero);
+      const float fa = inv * wa, fb = inv * wb;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        union {
+          uint32_t u;
+          T h[2];
+        } cv;
+        cv.u = sw[c];
+        const float e0 = __int_as_float(d[c][0]) - kMagicF, e1 = __int_as_float(d[c][1]) - kMagicF;
+        const float e2 = __int_as_float(d[c][2]) - kMagicF, e3 = __int_as_float(d[c][3]) - kMagicF;
+        ti[c][0] = fmaf(DT<T>::to_f(cv.h[0]), fmaf(fa, e0, fb * e1), ti[c][0]);   // column 16 (2 c + P) + g
+        ti[c][1] = fmaf(DT<T>::to_f(cv.h[1]), fmaf(fa, e2, fb * e3), ti[c][1]);   // column 16 (2 c + P) + g + 8
+      }
+      if (++slot == S) {
+        slot = 0;
+        phase ^= 1;
+      }
+    }
+    // the two digit pairs of a column sit in lanes tig and tig ^ 1
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v = ti[c][h] + __shfl_xor_sync(0xffffffffu, ti[c][h], 1);
+        if ((tig & 1) == 0) red[warp * BN + 16 * (2 * c + P) + g + 8 * h] = v;
+      }
+  } else if constexpr (kLdsm) {
     // The integer-ALU pipe (16 lanes per sub-partition) is this kernel's scarcest resource, so
     // the byte transposition is left to the load unit: ldmatrix.trans on 8x8 tiles of 16-bit elements gives
     // lane (g, tig) the word [B(2t,2g), B(2t,2g+1), B(2t+1,2g), B(2t+1,2g+1)] (B = packed byte, rows 2t, 2t+1
@@ -621,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 
   // ---------------- band sum of this CTA: cross-warp (k-group) reduction through shared memory
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < (kImma ? 0 : 8); ++j) {
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int tok = kM1 ? 0 : 2 * tig + (i & 1);
@@ -738,14 +825,16 @@ struct TpHint {
 };
 thread_local TpHint g_tp = {{}, 0, false};
 
-template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false>
+template <typename T, bool kTrick, bool kM1, int kPro, bool kHand = false, bool kImma = false>
 int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, Params prm,
                 int grid, int stages, bool pdl) {
   using C = Cfg<kM1>;
+  static_assert(!kImma || kM1, "the integer-MMA arithmetic is the one-token kernel's");
+  const size_t band = kImma ? static_cast<size_t>(prm.band_units) * (DIG_STAGE + DIG_INFO)
+                            : (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
   const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
-                      C::xred_bytes(prm.Z) + 16 * stages + 32 +
-                      (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
-  auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro, kHand>;
+                      C::xred_bytes(prm.Z) + 16 * stages + 32 + band;
+  auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro, kHand, kImma>;
   static size_t configured[64] = {0};
   int dev = 0;
   CGQ_CUDA_TRY(cudaGetDevice(&dev));
@@ -783,7 +872,17 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
 
 template <typename T, bool kTrick>
 int launch_m1(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS, const Params& prm,
-              int grid, int stages, bool pdl, int pro) {
+              int grid, int stages, bool pdl, int pro, bool imma) {
+  if (imma && prm.wait_ctr == nullptr && prm.signal_ctr == nullptr) {   // integer-MMA arithmetic (the default)
+    switch (pro) {
+      case PRO_RMSNORM:
+        return launch_inst<T, false, true, PRO_RMSNORM, false, true>(a, tmW, tmS, prm, grid, stages, pdl);
+      case PRO_SILU_GATE:
+        return launch_inst<T, false, true, PRO_SILU_GATE, false, true>(a, tmW, tmS, prm, grid, stages, pdl);
+      default:
+        return launch_inst<T, false, true, PRO_NONE, false, true>(a, tmW, tmS, prm, grid, stages, pdl);
+    }
+  }
   if (prm.wait_ctr != nullptr || prm.signal_ctr != nullptr) {   // tile-granular hand-over variant
     switch (pro) {
       case PRO_RMSNORM:
@@ -804,8 +903,11 @@ int launch_m1(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tmS,
   }
 }
 
+// arith: W4_ARITH_* (common.cuh)
 template <typename T>
-int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
+int launch_t(const GemmArgs& a, int arith, const GemvFused* fu) {
+  if (arith == W4_ARITH_DEFAULT) arith = default_w4_arith(W4_ARITH_DEFAULT);
+  const bool exact = arith == W4_ARITH_EXACT;
   const int G = a.K / 32;
   const int tiles = (a.N + BN - 1) / BN;
   static const int stages_env = env_int("CGQ_GEMV_STAGES", 0, 0, 16);
@@ -904,8 +1006,9 @@ int launch_t(const GemmArgs& a, bool exact, const GemvFused* fu) {
   constexpr bool kIsHalf = (DT<T>::code == CGQ_DTYPE_F16);
   const bool trick = kIsHalf && !exact;
   if (a.M == 1) {
-    if (trick) return launch_m1<T, kIsHalf>(a, tmW, tmS, prm, grid, stages, pdl, pro);
-    return launch_m1<T, false>(a, tmW, tmS, prm, grid, stages, pdl, pro);
+    const bool imma = arith == W4_ARITH_IMMA;
+    if (trick && !imma) return launch_m1<T, kIsHalf>(a, tmW, tmS, prm, grid, stages, pdl, pro, false);
+    return launch_m1<T, false>(a, tmW, tmS, prm, grid, stages, pdl, pro, imma);
   }
   // M > 1 in fp16 takes the subnormal-operand arithmetic too (8 % faster M = 8 chain).  It was switched off in round
   // 1 after run-to-run divergence at M >= 5; that was the ring-release race (mbarrier.arrive overtaking the stage's
@@ -925,15 +1028,23 @@ bool w4_gemv_supported(const GemmArgs& a) {
          al16(a.scale) && al16(a.A) && a.lda % 8 == 0 && true;
 }
 
-int launch_w4_gemv(const GemmArgs& a, bool exact) {
+int launch_w4_gemv(const GemmArgs& a, int arith) {
   static const bool umma_default = env_int("CGQ_GEMV_UMMA", 0, 0, 1) != 0;
-  if (umma_default && !exact && a.M == 1) {   // opt-in: integer tcgen05 decode kernel (gemv_w4_umma.cu)
+  if (umma_default && arith == W4_ARITH_DEFAULT && a.M == 1) {   // opt-in: integer tcgen05 decode kernel (gemv_w4_umma.cu)
     bool taken = false;
     const int rc = launch_w4_gemv_umma(a, &taken);
     if (rc != CGQ_OK || taken) return rc;
   }
-  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, exact, nullptr)
-                                  : launch_t<__nv_bfloat16>(a, exact, nullptr);
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, arith, nullptr)
+                                  : launch_t<__nv_bfloat16>(a, arith, nullptr);
+}
+
+// process-wide default arithmetic of the decode kernel: CGQ_GEMV_ARITH (0 imma, 1 exact, 2 subnormal) unless set
+// through cgq_set_decode_arith; returns the value in force before the call (set < 0: query only)
+int default_w4_arith(int set) {
+  static std::atomic<int> cur{env_int("CGQ_GEMV_ARITH", W4_ARITH_IMMA, W4_ARITH_IMMA, W4_ARITH_SUBNORMAL)};
+  if (set < W4_ARITH_IMMA || set > W4_ARITH_SUBNORMAL) return cur.load();
+  return cur.exchange(set);
 }
 
 void set_next_w4_hint(const void* w, const void* s, int N, int K) {
@@ -953,8 +1064,8 @@ int w4_gemv_tiles(int N) { return (N + BN - 1) / BN; }
 
 // M == 1 with a fused prologue (RMSNorm / SiLU-gate on the activation) and residual epilogue.
 int launch_w4_gemv_fused(const GemmArgs& a, const GemvFused& fu) {
-  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, false, &fu)
-                                  : launch_t<__nv_bfloat16>(a, false, &fu);
+  return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a, W4_ARITH_DEFAULT, &fu)
+                                  : launch_t<__nv_bfloat16>(a, W4_ARITH_DEFAULT, &fu);
 }
 
 }  // namespace cgq

@@ -12,7 +12,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_GEMV_UMMA, IMPL_SIMPLE, IMPL_TC  # noqa: F401
+from ._lib import (IMPL_AUTO, IMPL_GEMV, IMPL_GEMV_EXACT, IMPL_GEMV_IMMA, IMPL_GEMV_SUBNORMAL, IMPL_GEMV_UMMA,  # noqa: F401
+                   IMPL_SIMPLE, IMPL_TC)
 
 _DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1}
 _workspaces: dict[tuple[int, int], Tensor] = {}
@@ -270,6 +271,22 @@ def embedding_s8(ids: Tensor, weight: Tensor, weight_scale: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------- fused decode-step pieces
+class decode_arith:
+    """`with ops.decode_arith(_lib.ARITH_SUBNORMAL): ...` -- arithmetic of the int4 decode kernel for launches that do
+    not name one (cgq_set_decode_arith, include/cgq.h).  Process-wide: tests and A/B timing only."""
+
+    def __init__(self, arith: int):
+        self.arith = arith
+
+    def __enter__(self):
+        self.prev = _lib.load().cgq_set_decode_arith(self.arith)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().cgq_set_decode_arith(self.prev)
+        return False
+
+
 def gemv_fused_s4(a: Tensor, b: Tensor, b_scale: Tensor, bias: Tensor = None, resid: Tensor = None,
                   prologue: int = _lib.PRO_NONE, norm_weight: Tensor = None, eps: float = 0.0,
                   out: Tensor = None) -> Tensor:

@@ -40,10 +40,13 @@ extern "C" {
 /* Kernel selection for the *_ex entry points (tests / bench / profiling only). */
 #define CGQ_IMPL_AUTO 0             /* what cgq_w4a16_gemm / cgq_w8a16_gemm pick */
 #define CGQ_IMPL_SIMPLE 1           /* one-thread-per-column CUDA-core kernel, bit-faithful dequant */
-#define CGQ_IMPL_GEMV 2             /* TMA-fed cluster mma.sync kernel, M <= 8 (decode) */
-#define CGQ_IMPL_GEMV_EXACT 3       /* same, dequant via exact (q-8) fp16 subtraction instead of subnormal trick */
+#define CGQ_IMPL_GEMV 2             /* TMA-fed cluster mma.sync kernel, M <= 8 (decode), default arithmetic */
+#define CGQ_IMPL_GEMV_EXACT 3       /* same, (q-8) converted exactly to fp16 / bf16, f16 MMA */
 #define CGQ_IMPL_TC 4               /* tcgen05 tensor-core GEMM (prefill) */
 #define CGQ_IMPL_GEMV_UMMA 5        /* M == 1 decode on integer tcgen05 (int8 digits of the activation), opt-in */
+#define CGQ_IMPL_GEMV_SUBNORMAL 6   /* decode kernel, fp16 nibbles as subnormal f16 MMA operands (round-1/2 default) */
+#define CGQ_IMPL_GEMV_IMMA 7        /* decode kernel, M == 1: IMMA.16832 on base-128 digits of the activation (default);
+                                       M > 1 takes the subnormal-operand path */
 
 /* Library / ABI version: (major << 16) | minor. */
 int cgq_version(void);
@@ -368,6 +371,15 @@ int cgq_top_p_sample(const void* logits, int V, int dtype, int top_k, float top_
  * caller).  One-shot: the pointer is consumed by that launch.  NULL cancels.
  */
 void cgq_debug_trace(void* device_buffer);
+
+/*
+ * Arithmetic of the int4 decode kernel for launches that do not name one (cgq_w4a16_gemm, cgq_w4a16_gemv_fused,
+ * CGQ_IMPL_GEMV): 0 = IMMA.16832 on base-128 digits of the activation at M == 1 (default; CGQ_GEMV_ARITH overrides),
+ * 1 = exact (q - 8) conversion + f16 / bf16 MMA, 2 = fp16 nibbles as subnormal MMA operands.  Process-wide; returns
+ * the value in force before the call, any other `arith` only queries.  For tests / A-B timing (the persistent
+ * programs keep the subnormal arithmetic, their bit-identity tests select it for the launch-per-linear side).
+ */
+int cgq_set_decode_arith(int arith);
 
 #ifdef __cplusplus
 }

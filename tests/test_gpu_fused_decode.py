@@ -20,7 +20,7 @@ from util import assert_parity, from_torch, load_decode_golden, make_int4_case, 
 pytestmark = pytest.mark.gpu
 
 from chatglm_q_b200 import ops  # noqa: E402
-from chatglm_q_b200._lib import PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE  # noqa: E402
+from chatglm_q_b200._lib import ARITH_SUBNORMAL, PRO_NONE, PRO_RMSNORM, PRO_SILU_GATE  # noqa: E402
 from chatglm_q_b200.fused_decode import FusedDecodeModel, _FusedCache, accelerate  # noqa: E402
 
 DEV = "cuda"
@@ -270,7 +270,7 @@ def test_fused_step_tile_handover_bit_identical(cfg_kwargs):
         prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
         plain = FusedDecodeModel(model, max_len=64, handover=False)
         hand = FusedDecodeModel(model, max_len=64, handover=True)
-        with torch.no_grad():
+        with torch.no_grad(), ops.decode_arith(ARITH_SUBNORMAL):   # the kHand kernels keep the subnormal-operand arithmetic
             _, lg_p, kv_p = plain(input_ids=prompt, past_key_values=None)
             _, lg_h, kv_h = hand(input_ids=prompt, past_key_values=None)
             tok = lg_p[0, -1].argmax().reshape(1, 1)
@@ -385,8 +385,9 @@ def test_decode_program_bit_identical_to_per_linear_launches():
         emit(bf["x"], *head[:2], bf["logits"], prologue=PRO_RMSNORM, norm_weight=lnf, eps=1e-5)
 
     ref = buffers()
-    chain(lambda a, w, s, out, **kw: ops.gemv_fused_s4(a[:2 * w.shape[0] * (2 if kw.get("prologue") == PRO_SILU_GATE else 1)],
-                                                        w, s, out=out, **kw), ref)
+    with ops.decode_arith(ARITH_SUBNORMAL):     # the program keeps the subnormal-operand f16 arithmetic
+        chain(lambda a, w, s, out, **kw: ops.gemv_fused_s4(a[:2 * w.shape[0] * (2 if kw.get("prologue") == PRO_SILU_GATE else 1)],
+                                                            w, s, out=out, **kw), ref)
     torch.cuda.synchronize()
     got = buffers()
     prog = ops.DecodeProgram(torch.float16)

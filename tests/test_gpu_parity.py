@@ -21,7 +21,8 @@ from chatglm_q_b200 import ops  # noqa: E402
 
 DEV = "cuda"
 IMPLS4 = {"auto": ops.IMPL_AUTO, "simple": ops.IMPL_SIMPLE, "gemv": ops.IMPL_GEMV,
-          "gemv_exact": ops.IMPL_GEMV_EXACT, "tc": ops.IMPL_TC, "umma": ops.IMPL_GEMV_UMMA}
+          "gemv_exact": ops.IMPL_GEMV_EXACT, "tc": ops.IMPL_TC, "umma": ops.IMPL_GEMV_UMMA,
+          "gemv_subnormal": ops.IMPL_GEMV_SUBNORMAL, "gemv_imma": ops.IMPL_GEMV_IMMA}
 
 
 def u8(x):
@@ -120,7 +121,7 @@ def test_int8_linear_golden(golden, dtype):
 SHAPES4 = [(4096, 4608), (4096, 4096), (13696, 4096), (4096, 1280), (512, 256), (4096, 6848)]
 
 
-@pytest.mark.parametrize("impl", ["gemv", "gemv_exact", "simple"])
+@pytest.mark.parametrize("impl", ["gemv", "gemv_exact", "gemv_subnormal", "gemv_imma", "simple"])
 @pytest.mark.parametrize("kind", ["Q", "R"])
 @pytest.mark.parametrize("m", [1, 2, 5, 8])
 def test_int4_decode_shapes(impl, kind, m):
@@ -164,6 +165,34 @@ def test_int4_decode_big_shapes(dtype):
         bias = orc.round_to(np.random.default_rng(n).standard_normal(n) * 0.1, dtype) if with_bias else None
         want = c_oracle.w4a16_gemm(a, bq, s, bias, dtype)
         assert_parity(run4(a, bq, s, dtype, bias=bias), want, f"int4 big {dtype} M={m} N={n}", rtol=rtol_for(dtype))
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_int4_imma_digits_are_fp32_exact(dtype):
+    """The integer-MMA arithmetic (base-128 digits of the activation) against the fp64 value of the
+    same sum of products, BEFORE the final rounding matters: activations spanning 20 binades inside one quantisation
+    group (outliers next to tiny values), a subnormal-only group, an all-zero group, a ragged last column tile.  The
+    result must equal the correctly rounded fp64 sum up to 1 ulp of the 16-bit output (fp32 accumulation error only)."""
+    k, n = 4096, 4608 + 16
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((1, k)) * np.exp2(rng.integers(-14, 6, size=(1, k)))
+    a[0, 64:96] = 0.0                                   # all-zero group
+    a[0, 96:128] = rng.integers(-3, 4, size=32) * 2.0 ** -24 if dtype == "float16" else 1e-30   # subnormals / vanishing
+    a[0, 1000] = 3.0e4                                  # outlier: 2^15 next to 2^-14 in one group
+    a = orc.round_to(a, dtype)
+    _, bq, s = make_int4_case(78, 1, k, n, "R", dtype)
+    w = orc.unpack_int4_i8(bq).astype(np.float64).reshape(k // 32, 32, n) * s.astype(np.float64)[:, None, :]
+    exact = a.astype(np.float64) @ w.reshape(k, n)
+    for impl in ("gemv_imma", "auto"):
+        got = run4(a, bq, s, dtype, impl=IMPLS4[impl]).astype(np.float64)
+        ulp = np.maximum(np.abs(exact), 2.0 ** -14) * (2.0 ** -10 if dtype == "float16" else 2.0 ** -7)
+        assert (np.abs(got - exact) <= 0.5001 * ulp + 2e-6 * np.abs(a).astype(np.float64) @ np.abs(w.reshape(k, n))).all(), impl
+    # non-finite activations poison the output like the reference's matmul does (never a finite garbage value)
+    a2 = a.copy()
+    a2[0, 5] = np.inf
+    assert not np.isfinite(run4(a2, bq, s, dtype, impl=IMPLS4["gemv_imma"])).any()
+    a2[0, 5] = np.nan
+    assert np.isnan(run4(a2, bq, s, dtype, impl=IMPLS4["gemv_imma"])).all()
 
 
 @pytest.mark.parametrize("kind", ["Q", "R"])
