@@ -225,10 +225,32 @@ __device__ __forceinline__ float tp_allreduce(const cgq_tp_ctx& tp, unsigned idx
   return sum;
 }
 // final value of output column n: (all-reduce) -> round -> bias -> residual -> store (to every rank for tp.out)
+// bias[n] / resid[n] of the column a consumer thread will store, requested right after the activation band is staged:
+// the tail of a 4 us launch should not wait for one more L2 round trip
 template <typename T>
-__device__ __forceinline__ void store_column(const Params& p, float acc, int n, int step_no) {
+struct ColPre {
+  T bias, resid;
+};
+template <typename T>
+__device__ __forceinline__ ColPre<T> preload_column(const Params& p, int n) {
+  ColPre<T> c;
+  c.bias = c.resid = DT<T>::from_f(0.f);
+  uint16_t b = 0, r = 0;
+  if (n < p.N) {
+    if (p.bias != nullptr) asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(b) : "l"(static_cast<const T*>(p.bias) + n));
+    if (p.resid != nullptr) asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(static_cast<const T*>(p.resid) + n));
+  }
+  c.bias = reinterpret_cast<const T&>(b);
+  c.resid = reinterpret_cast<const T&>(r);
+  return c;
+}
+template <typename T>
+__device__ __forceinline__ void store_column(const Params& p, float acc, int n, int step_no, const ColPre<T>& pre) {
   if (p.tp.world > 1 && p.tp.recv[0] != nullptr) acc = tp_allreduce(p.tp, p.tp_idx, step_no, acc, n);
-  const T val = add_resid<T>(epilogue<T>(acc, static_cast<const T*>(p.bias), n), static_cast<const T*>(p.resid), n);
+  // round -> (+ bias, rounded) -> (+ residual, rounded): epilogue<T> / add_resid<T> on the preloaded values
+  T val = DT<T>::from_f(acc);
+  if (p.bias != nullptr) val = DT<T>::from_f(DT<T>::to_f(val) + DT<T>::to_f(pre.bias));
+  if (p.resid != nullptr) val = DT<T>::from_f(DT<T>::to_f(pre.resid) + DT<T>::to_f(val));
   if (p.tp.world > 1 && p.tp.out[0] != nullptr) {
     for (int r = 0; r < p.tp.world; ++r) static_cast<T*>(p.tp.out[r])[p.tp.out_offset + n] = val;
   } else {
@@ -253,8 +275,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   float* xred = reinterpret_cast<float*>(gen + off_red + C::RED_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_red + C::RED_BYTES + C::xred_bytes(p.Z));
   uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;    // rank 0: completes when the band sums of ranks 1 .. Z-1 have landed in xred
   // M == 1: activation band of this CTA (band_units x 128 k, zero beyond K), staged by the consumers
-  const uint32_t off_band = (off_red + C::RED_BYTES + C::xred_bytes(p.Z) + 16u * S + 15u) & ~15u;
+  const uint32_t off_band = (off_red + C::RED_BYTES + C::xred_bytes(p.Z) + 16u * S + 16u + 15u) & ~15u;
   const uint32_t Aband = base + off_band;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -268,6 +291,9 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   if (kM1 && p.tp.world > 1 && p.tp.step != nullptr)
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(step_no) : "l"(p.tp.step));
 
+  ColPre<T> pre;
+  pre.bias = pre.resid = DT<T>::from_f(0.f);
+
   // ---- prologue: barriers
   if (threadIdx.x == CW * 32) {
     ptx::prefetch_tmap(&tmW);
@@ -275,6 +301,11 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], CW);
+    }
+    if (p.Z > 1 && z == 0) {
+      // the remote stores carry the arrival (st.async ... complete_tx): expected bytes = every other rank's band sums
+      ptx::mbar_init(xbar, 1);
+      ptx::mbar_expect_tx(xbar, static_cast<uint32_t>(p.Z - 1) * static_cast<uint32_t>(min(p.M, MR)) * BN * 4u);
     }
     ptx::fence_mbar_init();
   }
@@ -348,11 +379,16 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       // band; the chunks a thread loads for the sum stay in registers and are the ones it normalises
       constexpr int U = 4;
       const bool single = nchunk <= U * CW * 32;
+      // kImma, several bands per tile: the digit conversion costs ~150 instructions per chunk, so the band's chunks
+      // are dealt evenly to the 128 threads in a second pass (the raw chunks cross through shared memory) instead of
+      // staying with whichever thread loaded them for the sum (at Z = 8 that is 1 thread in 8)
+      const bool deal = kImma && single && Z > 1;
+      const uint32_t raw = Aband + p.band_units * (DIG_STAGE + DIG_INFO);
       const T* nw = static_cast<const T*>(p.norm_w);
       uint4 xr[U], wr[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {  // the norm weight does not depend on the previous kernel
-        const int c = tid + CW * 32 * i;
+        const int c = deal ? c_lo + tid + CW * 32 * i : tid + CW * 32 * i;
         wr[i] = (single && c >= c_lo && c < c_hi && c < nchunk) ? ldnc128(nw + c * 8) : zero;
       }
       wait_inputs<kHand>(p);
@@ -367,6 +403,13 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 #pragma unroll
         for (int i = 0; i < U; ++i) ss += sumsq8<T>(xr[i]);
       }
+      if (deal) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int c = tid + CW * 32 * i;
+          if (c >= c_lo && c < c_hi) ptx::sts128(raw + (c - c_lo) * 16, xr[i]);
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       if (lane == 0) red[warp] = ss;
@@ -375,7 +418,17 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 #pragma unroll
       for (int w = 0; w < CW; ++w) tot_ss += red[w];
       const float rstd = rsqrtf(tot_ss / static_cast<float>(p.K) + p.eps);
-      if (single) {
+      if (deal) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {   // the band is at most the row: U passes cover it
+          if (c_lo + CW * 32 * i < c_hi) {
+            const int c = c_lo + tid + CW * 32 * i;
+            const bool in = c < c_hi, ld = in && c < nchunk;
+            const uint4 x = ld ? ptx::lds128(raw + (c - c_lo) * 16) : zero;
+            put(c, in, ld ? rmsnorm8<T>(x, wr[i], rstd) : zero);
+          }
+        }
+      } else if (single) {
 #pragma unroll
         for (int i = 0; i < U; ++i) {
           const int c = tid + CW * 32 * i;
@@ -399,6 +452,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
         put(c, c < c_hi, v);
       }
     }
+    if (Z == 1 || z == 0) pre = preload_column<T>(p, tile * BN + tid);
     ptx::named_bar_sync(1, CW * 32);
   } else {
     ptx::pdl_wait_prior_grid();
@@ -733,7 +787,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       const int n = tile * BN + t;
       if (n < p.N) {
         if constexpr (kM1) {
-          store_column<T>(p, v[0], n, step_no);
+          store_column<T>(p, v[0], n, step_no, pre);
         } else {
           T* Cp = static_cast<T*>(p.C);
           const T* bias = static_cast<const T*>(p.bias);
@@ -744,39 +798,39 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       }
       signal_tile<kHand>(p);
     } else {
-      // push the band sum into rank 0's shared memory (DSMEM); rank 0 adds them in rank order
+      // The band sums meet in rank 0's shared memory (DSMEM).  Ranks 1 .. Z-1 push theirs with st.async, which
+      // completes the transaction count of rank 0's mbarrier: the data is its own arrival signal, no cluster barrier
+      // at the end of a 4 us launch, and the pushing CTA exits right away.  Rank 0 adds in rank order.
       ptx::cluster_wait_acquire();               // every CTA of the cluster has started (phase A)
-      const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>((z * MR) * BN + t) * 4u;
-      const uint32_t remote = ptx::mapa_rank(local, 0);
+      if (z != 0) {
+        const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>((z * MR) * BN + t) * 4u;
+        const uint32_t remote = ptx::mapa_rank(local, 0), rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
 #pragma unroll
-      for (int m = 0; m < MR; ++m)
-        if (m < p.M) ptx::st_cluster_f32(remote + m * BN * 4, v[m]);
+        for (int m = 0; m < MR; ++m)
+          if (m < p.M) ptx::st_async_cluster_f32(remote + m * BN * 4, v[m], rbar);
+      } else {
+        ptx::mbar_wait(xbar, 0);
+        const int n = tile * BN + t;
+        if (n < p.N) {
+          T* Cp = static_cast<T*>(p.C);
+          const T* bias = static_cast<const T*>(p.bias);
+#pragma unroll
+          for (int m = 0; m < MR; ++m) {
+            if (m < p.M) {
+              float acc = v[m];
+              for (int zz = 1; zz < Z; ++zz) acc += xred[(zz * MR + m) * BN + t];
+              if constexpr (kM1)
+                store_column<T>(p, acc, n, step_no, pre);
+              else
+                Cp[m * p.ldc + n] = epilogue<T>(acc, bias, n);
+            }
+          }
+        }
+        signal_tile<kHand>(p);
+      }
     }
   }
   }  // consumers
-  if (Z > 1) {
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-    if (z == 0 && threadIdx.x < BN) {
-      const int t = threadIdx.x, n = tile * BN + t;
-      if (n < p.N) {
-        T* Cp = static_cast<T*>(p.C);
-        const T* bias = static_cast<const T*>(p.bias);
-#pragma unroll
-        for (int m = 0; m < MR; ++m) {
-          if (m < p.M) {
-            float acc = 0.f;
-            for (int zz = 0; zz < Z; ++zz) acc += xred[(zz * MR + m) * BN + t];
-            if constexpr (kM1)
-              store_column<T>(p, acc, n, step_no);
-            else
-              Cp[m * p.ldc + n] = epilogue<T>(acc, bias, n);
-          }
-        }
-      }
-      signal_tile<kHand>(p);     // threads 0 .. BN-1 are exactly the CW consumer warps
-    }
-  }
   if (threadIdx.x == 0) stamp(p, 5);
 }
 
@@ -830,10 +884,12 @@ int launch_inst(const GemmArgs& a, const CUtensorMap& tmW, const CUtensorMap& tm
                 int grid, int stages, bool pdl) {
   using C = Cfg<kM1>;
   static_assert(!kImma || kM1, "the integer-MMA arithmetic is the one-token kernel's");
-  const size_t band = kImma ? static_cast<size_t>(prm.band_units) * (DIG_STAGE + DIG_INFO)
+  // (+ the raw chunks of the band while the RMSNorm prologue deals them to the threads, Z > 1 only)
+  const size_t band = kImma ? static_cast<size_t>(prm.band_units) *
+                                  (DIG_STAGE + DIG_INFO + (kPro == PRO_RMSNORM && prm.Z > 1 ? KSTAGE * 2 : 0))
                             : (kM1 ? static_cast<size_t>(prm.band_units) * KSTAGE * 2 : 0);
   const size_t smem = 1024 + static_cast<size_t>(stages) * C::STAGE_BYTES + C::RED_BYTES +
-                      C::xred_bytes(prm.Z) + 16 * stages + 32 + band;
+                      C::xred_bytes(prm.Z) + 16 * stages + 48 + band;
   auto kern = w4_gemv_kernel<T, kTrick, kM1, kPro, kHand, kImma>;
   static size_t configured[64] = {0};
   int dev = 0;

@@ -134,6 +134,13 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
+// remote store that completes `bytes` of the transaction count of an mbarrier in the SAME remote CTA: the data is its
+// own arrival signal (no cluster barrier, the storing CTA may exit right away)
+__device__ __forceinline__ void st_async_cluster_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "r"(__float_as_uint(v)), "r"(cluster_mbar)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }

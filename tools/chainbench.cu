@@ -159,6 +159,10 @@ int main(int argc, char** argv) {
     size_t per = (size_t)K * N / 2 + (size_t)(K / 32) * N * 2;
     int copies = (int)std::max<size_t>(2, (400u << 20) / per + 1);
     if (M > 8) copies = std::min(copies, 4);
+    // CGQ_SINGLE_COPIES=1: the same weights every launch, i.e. L2-resident after the first one (what a perfect L2
+    // prefetcher would give the kernel)
+    const int launches = copies;
+    if (getenv("CGQ_SINGLE_COPIES")) copies = std::max(1, atoi(getenv("CGQ_SINGLE_COPIES")));
     std::vector<Lin> ls;
     for (int i = 0; i < copies; ++i) ls.push_back(make_lin(K, N, false, 77 + 3 * i));
     __half *x, *y;
@@ -171,14 +175,14 @@ int main(int argc, char** argv) {
     cudaGraph_t g;
     cudaGraphExec_t ge;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < copies; ++i) {
+    for (int i = 0; i < launches; ++i) {
       if (M <= 8) hint(ls[(i + 1) % copies]);
-      run_lin(ls[i], x, y, M, K, st);
+      run_lin(ls[i % copies], x, y, M, K, st);
     }
     CK(cudaStreamEndCapture(st, &g));
     CK(cudaGraphInstantiate(&ge, g, 0));
     float ms = time_graph(ge, st, reps);
-    double us = ms * 1e3 / copies;
+    double us = ms * 1e3 / launches;
     double by = (double)ls[0].bytes(M), fl = 2.0 * M * N * (double)K;
     printf("single M=%d K=%d N=%d copies=%d: %.2f us/launch  %.1f GB/s  %.2f TFLOP/s\n", M, K, N,
            copies, us, by / us / 1e3, fl / us / 1e6);
