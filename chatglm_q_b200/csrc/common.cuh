@@ -107,7 +107,7 @@ void set_w4_tp(const cgq_tp_ctx& ctx, unsigned idx);
 int w4_gemv_tiles(int N);
 int launch_w8_simple(const GemmArgs& a);
 // arithmetic of the int4 decode kernel (gemv_w4.cu).  DEFAULT = CGQ_GEMV_ARITH (0 = IMMA unless set): integer MMA on
-// base-128 digits of the activation at M == 1, the subnormal-operand f16 MMA at M > 1; EXACT = (q - 8) converted
+// base-256 digits of the activation at M == 1, the subnormal-operand f16 MMA at M > 1; EXACT = (q - 8) converted
 // exactly to T, f16 / bf16 MMA; SUBNORMAL = fp16 nibbles as subnormal operands at every M (round-1/2 kernel).
 enum { W4_ARITH_DEFAULT = -1, W4_ARITH_IMMA = 0, W4_ARITH_EXACT = 1, W4_ARITH_SUBNORMAL = 2 };
 int launch_w4_gemv(const GemmArgs& a, int arith);

@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
 #pragma unroll
         for (int i = 0; i < U; ++i) ss += sumsq8<T>(xr[i]);
       }
+      if (threadIdx.x == 0 && ss >= 0.f) stamp(p, 6);     // the row has arrived from L2 (the stamp waits for the sum)
       if (deal) {
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     }
     if (Z == 1 || z == 0) pre = preload_column<T>(p, tile * BN + tid);
     ptx::named_bar_sync(1, CW * 32);
+    if (threadIdx.x == 0) stamp(p, 7);       // activation band staged
   } else {
     ptx::pdl_wait_prior_grid();
     if (threadIdx.x == 0) stamp(p, 2);
@@ -475,14 +477,14 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
     // 16 jj + g and 16 jj + g + 8, i.e. one 32-bit A-fragment register of IMMA.16832 per output column, and
     // `word & 0x0F0F0F0F` / `word & 0xF0F0F0F0` are its even-k nibbles q and its odd-k nibbles as 16 q: TWO
     // integer-pipe instructions per 8 weights (the f16 path needs five) and one MMA per 512 (f16: 256).
-    // The activation enters as four signed base-128 digits per element (put_digits) in MMA columns 0-3 / 4-7:
+    // The activation enters as four signed base-256 digits per element (put_digits) in MMA columns 0-3 / 4-7:
     // the MMA of an even jj carries them in columns 0-3, the MMA of jj + 1 in columns 4-7 and accumulates onto the
     // first one's result, so all 32 lanes own live accumulators (lane tig: digits 2 (tig & 1), + 1 of column block
     // jj = 2 c + (tig >> 1)).  The accumulator starts from kMagicI - 8 (sum_even d + 16 sum_odd d), the -8 offset
     // of the nibbles, produced by one extra MMA against constant (-8, -128) rows: the s32 result IS the fp32
     // number 1.5 2^23 + sum, one FADD away from the exact integer group sum -- no I2F on the quarter-rate pipe.
     const int P = tig >> 1;
-    const float wa = (tig & 1) ? 128.f : 2097152.f, wb = (tig & 1) ? 1.f : 16384.f;   // weights of this lane's digits
+    const float wa = (tig & 1) ? 65536.f : 1.f, wb = (tig & 1) ? 16777216.f : 256.f;   // weights of this lane's digits
     const uint32_t m0 = g < 4 ? 0xFFFFFFFFu : 0u;                  // this lane's B column is a digit of block P = 0 / 1
     const int lrow = 16 * warp + (lane & 15);
     uint32_t ld_off[4];

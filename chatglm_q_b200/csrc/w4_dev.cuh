@@ -125,12 +125,13 @@ __device__ __forceinline__ uint4 silu_gate8(const uint4& h, const uint4& g) {
   }
   return o;
 }
-// ---- integer-MMA arithmetic of the one-token kernel (gemv_w4.cu, kImma): the activation as base-128 digits --------
+// ---- integer-MMA arithmetic of the one-token kernel (gemv_w4.cu, kImma): the activation as base-256 digits --------
 // A 32-k quantisation group of the activation row is scaled by a power of two so that its largest magnitude lands in
-// [2^26, 2^27) and every element becomes the integer X = d0 2^21 + d1 2^14 + d2 2^7 + d3 with balanced digits
-// |d| <= 64 (signed bytes: the B operand of IMMA.16832.U8.S8).  fp16 / bf16 elements down to 2^-16 of the group's
-// maximum are represented EXACTLY, smaller ones to 2^-28 of it -- below the rounding of the fp32 accumulation.  The odd
-// k of a byte pair enter divided by 16, because the high nibble is used in place as the unsigned byte 16 q.
+// [2^29, 2^30) and every element becomes the integer X = s3 2^24 + s2 2^16 + s1 2^8 + s0 with SIGNED bytes s_i (the B
+// operand of IMMA.16832.U8.S8): X + 0x00808080 has the bytes s_i + 128 (s3: as is), one add and one xor after the
+// float -> int conversion.  fp16 / bf16 elements down to 2^-19 of the group's maximum are represented EXACTLY, smaller
+// ones to 2^-30 of it -- far below the rounding of the fp32 accumulation.  The odd k of a byte pair enter divided by
+// 16, because the high nibble is used in place as the unsigned byte 16 q.
 constexpr int DIG_STAGE = CW * 4 * 32;        // bytes of digits per k-stage: [group][digit][tig] x (b0, b1)
 constexpr int DIG_INFO = CW * 4;              // + one fp32 per group: 2^-shift
 constexpr float kMagicF = 12582912.f;         // 1.5 * 2^23: fp32 whose mantissa field is a two's-complement integer
@@ -148,39 +149,32 @@ __device__ __forceinline__ void put_digits(uint32_t dig_base, uint32_t info_base
   mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
   mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
   // biased fp32 exponent of the maximum's binade
-  uint32_t mb = kHalf ? max(mx >> 10, 1u) + 112u : max(mx >> 7, 27u);
+  uint32_t mb = kHalf ? max(mx >> 10, 1u) + 112u : max(mx >> 7, 30u);
   const bool bad = kHalf ? (mx >> 10) == 31u : (mx >> 7) == 255u;     // inf / NaN in the group: poison its sums
   if (bad) mb = 127u;
-  const float sc = __uint_as_float((280u - mb) << 23);                 // max * sc in [2^26, 2^27)
+  const float sc = __uint_as_float((283u - mb) << 23);                 // max * sc in [2^29, 2^30)
   const float sc16 = sc * 0.0625f;
   const T* h = reinterpret_cast<const T*>(&v);
-  uint32_t y[4][8];
+  uint32_t z[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float xs = DT<T>::to_f(h[i]) * ((i & 1) ? sc16 : sc);        // exact (power of two)
-    const float y0 = fmaf(xs, 1.f / 2097152.f, kMagicF);
-    const float r1 = fmaf(y0 - kMagicF, -2097152.f, xs);
-    const float y1 = fmaf(r1, 1.f / 16384.f, kMagicF);
-    const float r2 = fmaf(y1 - kMagicF, -16384.f, r1);
-    const float y2 = fmaf(r2, 1.f / 128.f, kMagicF);
-    const float r3 = fmaf(y2 - kMagicF, -128.f, r2);
-    const float y3 = r3 + kMagicF;
-    y[0][i] = __float_as_uint(y0);
-    y[1][i] = __float_as_uint(y1);
-    y[2][i] = __float_as_uint(y2);
-    y[3][i] = __float_as_uint(y3);
+    int x;
+    asm("cvt.rni.sat.s32.f32 %0, %1;" : "=r"(x) : "f"(DT<T>::to_f(h[i]) * ((i & 1) ? sc16 : sc)));   // exact scaling
+    z[i] = (static_cast<uint32_t>(x) + 0x00808080u) ^ 0x00808080u;     // bytes = signed digits, least significant first
   }
   if (store) {
     const int st = chunk >> 4, grp = (chunk >> 2) & 3, tg = chunk & 3;
     const uint32_t dst = dig_base + st * DIG_STAGE + grp * 128 + tg * 8;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      // low byte of each y = the digit; even k -> b0, odd k -> b1
-      const uint32_t e01 = __byte_perm(y[d][0], y[d][2], 0x0040), e23 = __byte_perm(y[d][4], y[d][6], 0x0040);
-      const uint32_t o01 = __byte_perm(y[d][1], y[d][3], 0x0040), o23 = __byte_perm(y[d][5], y[d][7], 0x0040);
-      ptx::sts64(dst + d * 32, __byte_perm(e01, e23, 0x5410), __byte_perm(o01, o23, 0x5410));
-    }
-    if (tg == 0) ptx::sts32(info_base + st * DIG_INFO + grp * 4, bad ? 0x7FC00000u : (mb - 26u) << 23);
+    // 4 x 4 byte transposes: even k -> b0 words, odd k -> b1 words, one word per digit
+    const uint32_t e01a = __byte_perm(z[0], z[2], 0x5140), e23a = __byte_perm(z[4], z[6], 0x5140);
+    const uint32_t e01b = __byte_perm(z[0], z[2], 0x7362), e23b = __byte_perm(z[4], z[6], 0x7362);
+    const uint32_t o01a = __byte_perm(z[1], z[3], 0x5140), o23a = __byte_perm(z[5], z[7], 0x5140);
+    const uint32_t o01b = __byte_perm(z[1], z[3], 0x7362), o23b = __byte_perm(z[5], z[7], 0x7362);
+    ptx::sts64(dst + 0, __byte_perm(e01a, e23a, 0x5410), __byte_perm(o01a, o23a, 0x5410));
+    ptx::sts64(dst + 32, __byte_perm(e01a, e23a, 0x7632), __byte_perm(o01a, o23a, 0x7632));
+    ptx::sts64(dst + 64, __byte_perm(e01b, e23b, 0x5410), __byte_perm(o01b, o23b, 0x5410));
+    ptx::sts64(dst + 96, __byte_perm(e01b, e23b, 0x7632), __byte_perm(o01b, o23b, 0x7632));
+    if (tg == 0) ptx::sts32(info_base + st * DIG_INFO + grp * 4, bad ? 0x7FC00000u : (mb - 29u) << 23);
   }
 }
 

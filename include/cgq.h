@@ -45,7 +45,7 @@ extern "C" {
 #define CGQ_IMPL_TC 4               /* tcgen05 tensor-core GEMM (prefill) */
 #define CGQ_IMPL_GEMV_UMMA 5        /* M == 1 decode on integer tcgen05 (int8 digits of the activation), opt-in */
 #define CGQ_IMPL_GEMV_SUBNORMAL 6   /* decode kernel, fp16 nibbles as subnormal f16 MMA operands (round-1/2 default) */
-#define CGQ_IMPL_GEMV_IMMA 7        /* decode kernel, M == 1: IMMA.16832 on base-128 digits of the activation (default);
+#define CGQ_IMPL_GEMV_IMMA 7        /* decode kernel, M == 1: IMMA.16832 on base-256 digits of the activation (default);
                                        M > 1 takes the subnormal-operand path */
 
 /* Library / ABI version: (major << 16) | minor. */
@@ -374,7 +374,7 @@ void cgq_debug_trace(void* device_buffer);
 
 /*
  * Arithmetic of the int4 decode kernel for launches that do not name one (cgq_w4a16_gemm, cgq_w4a16_gemv_fused,
- * CGQ_IMPL_GEMV): 0 = IMMA.16832 on base-128 digits of the activation at M == 1 (default; CGQ_GEMV_ARITH overrides),
+ * CGQ_IMPL_GEMV): 0 = IMMA.16832 on base-256 digits of the activation at M == 1 (default; CGQ_GEMV_ARITH overrides),
  * 1 = exact (q - 8) conversion + f16 / bf16 MMA, 2 = fp16 nibbles as subnormal MMA operands.  Process-wide; returns
  * the value in force before the call, any other `arith` only queries.  For tests / A-B timing (the persistent
  * programs keep the subnormal arithmetic, their bit-identity tests select it for the launch-per-linear side).

@@ -169,7 +169,7 @@ def test_int4_decode_big_shapes(dtype):
 
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 def test_int4_imma_digits_are_fp32_exact(dtype):
-    """The integer-MMA arithmetic (base-128 digits of the activation) against the fp64 value of the
+    """The integer-MMA arithmetic (base-256 digits of the activation) against the fp64 value of the
     same sum of products, BEFORE the final rounding matters: activations spanning 20 binades inside one quantisation
     group (outliers next to tiny values), a subnormal-only group, an all-zero group, a ragged last column tile.  The
     result must equal the correctly rounded fp64 sum up to 1 ulp of the 16-bit output (fp32 accumulation error only)."""

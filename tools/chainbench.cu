@@ -390,10 +390,10 @@ int main(int argc, char** argv) {
                    sum / cnt / 1e3, (mx - t00) / 1e3);
         }
       }
-      const char* names[8] = {"entry", "producer", "depwait", "firstdata", "loopend", "exit", "-", "-"};
+      const char* names[8] = {"entry", "producer", "depwait", "firstdata", "loopend", "exit", "rowloaded", "staged"};
       for (size_t k = 4; k < 13; ++k) {
         printf("linear %zu (K=%d N=%d):\n", k, ls[k].K, ls[k].N);
-        for (int w = 0; w < 6; ++w) {
+        for (int w = 0; w < 8; ++w) {
           uint64_t mn = ~0ull, mx = 0;
           double sum = 0;
           int cnt = 0;
@@ -675,7 +675,7 @@ int main(int argc, char** argv) {
     uint64_t t00 = ~0ull;
     for (size_t i = 0; i < h.size(); i += kTraceWords)
       if (h[i]) t00 = std::min(t00, h[i]);
-    const char* names[8] = {"entry", "prolog", "depwait", "firstdata", "loopend", "exit", "fix_atomic", "fix_loaded"};
+    const char* names[8] = {"entry", "prolog", "depwait", "firstdata", "loopend", "exit", "rowloaded", "staged"};
     for (size_t k = 0; k < std::min<size_t>(ls.size(), 9); ++k) {
       printf("kernel %zu (K=%d N=%d):\n", k, ls[k].K, ls[k].N);
       for (int w = 0; w < kTraceWords; ++w) {
