@@ -85,6 +85,12 @@ struct AttnParams {
   int n_head, n_groups, max_len;
   int splits;          // CTAs per head (cluster size): the context is dealt to them in blocks of 16 rows
   unsigned long long* trace;  // optional timeline (cgq_debug_trace), 8 words per CTA
+  // K / V caches of the NEXT attention launch of the step (cgq_attention_next_kv) or null: their live rows are
+  // requested into L2 one layer ahead.  A cache row is touched once per token and 3.4 GB of weights stream through
+  // L2 in between, so every step finds it in HBM -- and the loads of a launch queue behind the ~20 MB of weight
+  // requests the neighbouring linears keep in flight (2.9 us before the first score at a context of 96 rows).
+  const void* next_k;
+  const void* next_v;
 };
 
 __device__ __forceinline__ void attn_stamp(const AttnParams& p, int slot) {
@@ -97,7 +103,7 @@ __device__ __forceinline__ void attn_stamp(const AttnParams& p, int slot) {
 
 constexpr int kAttnThreads = 512;
 constexpr int kAttnWarps = kAttnThreads / 32;
-constexpr int kRowsPerIter = 8;   // cache rows a warp has in flight
+constexpr int kPrefetchIters = 4;   // row batches (32 / LPR rows per warp each) a lane has in flight before the dependency wait
 
 // activations written by the previous kernel of the chain are read past L1 (a stale line from an earlier
 // layer's use of the same buffer must never be hit)
@@ -112,47 +118,26 @@ __device__ __forceinline__ int ldcg_i32(const int* p) {
   asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-
-// One cache row = 32 lanes x EPL elements.  The load is kept raw (registers) so that many rows can be in
-// flight before the first conversion waits on one of them.
-template <int EPL>
-struct RawRow {
-  uint32_t w[EPL / 2];
-};
-template <typename T, int EPL>
-__device__ __forceinline__ RawRow<EPL> load_raw(const T* row, int lane) {
-  RawRow<EPL> r;
-  if (EPL == 4) {
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[EPL / 2 - 1]) : "l"(row + lane * 4));
-  } else {
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r.w[0]) : "l"(row + lane * 2));
-  }
-  return r;
-}
-template <typename T, int EPL>
-__device__ __forceinline__ void cvt_row(const RawRow<EPL>& r, float (&f)[EPL]) {
-  const T* h = reinterpret_cast<const T*>(r.w);
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) f[e] = DT<T>::to_f(h[e]);
-}
-template <typename T, int EPL>
-__device__ __forceinline__ void load_row(const T* row, int lane, float (&f)[EPL]) {
-  cvt_row<T, EPL>(load_raw<T, EPL>(row, lane), f);
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+__device__ __forceinline__ uint4 ldcg_128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-// One query row, one head = one CLUSTER of S CTAs (S = p.splits in {1,2,4,8}).  The cached rows are dealt
-// to the CTAs in blocks of kAttnWarps rows (block b -> CTA b % S, row b*16 + warp -> that CTA's warp), so
-// every context length is balanced.  Each warp keeps an online softmax (running max, sum, un-normalised
-// output) over its rows; warps are combined through shared memory and cluster ranks through distributed
-// shared memory, both in a fixed order (deterministic).
+
+// One query row, one head = one CLUSTER of S CTAs (S = p.splits in {1,2,4,8}).
+// A warp works on RPW = 256 / DH cached rows at a time: lane = (row slot `sub` = lane / LPR, column chunk `c` =
+// lane % LPR), a lane holds 8 consecutive elements of its row (one 16-byte load; a dot product is 8 FMAs and
+// log2(LPR) shuffle steps for RPW rows, where one row per warp needed five steps per row -- the shuffle chain, not the
+// cache, bounded the old kernel: 2.3 us for 96 rows).  Row batch i of warp w on cluster rank r: rows
+// ((i S + r) 16 + w) RPW + sub, so every context length is balanced over warps and ranks.  Each row slot keeps an
+// online softmax (running max, sum, un-normalised output) in registers; slots are merged by shuffles, warps through
+// shared memory and cluster ranks through distributed shared memory, all in a fixed order (deterministic).
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const AttnParams p) {
-  constexpr int EPL = DH / 32;
+  constexpr int EPL = 8;               // elements of a row per lane: one 16-byte load
+  constexpr int NV = 1;
+  constexpr int LPR = DH / EPL;        // lanes per row
+  constexpr int RPW = 32 / LPR;        // rows per warp and batch
   constexpr int kMaxSplit = 8;
   extern __shared__ float sm[];
   float* q_s = sm;                       // rotated, scaled query (T-rounded values)
@@ -168,6 +153,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   const int hpg = p.n_head / p.n_groups;
   const int g = h / hpg;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int sub = lane / LPR, c = lane % LPR;
   attn_stamp(p, 0);
   if (p.splits > 1) ptx::cluster_arrive_release();   // phase A: waited for before the first DSMEM store (racecheck)
   ptx::pdl_launch_dependents();
@@ -182,19 +168,34 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   T* vc = static_cast<T*>(p.vcache);
   const size_t row_stride = static_cast<size_t>(p.n_groups) * DH;
   const bool writer = (h % hpg) == 0 && rank == 0;
-  const T* kbase = kc + g * DH;
-  const T* vbase = vc + g * DH;
-  // i-th block of this CTA -> cached row of this warp
-  auto row_of = [&](int i) { return (i * S + rank) * kAttnWarps + warp; };
-  const int nblk = live ? (n_past + kAttnWarps - 1) / kAttnWarps : 0;      // blocks of cached rows, all CTAs
-  const int my_blk = nblk > rank ? (nblk - rank + S - 1) / S : 0;          // ... dealt to this CTA
-  RawRow<EPL> k0raw[kRowsPerIter], v0raw[kRowsPerIter];
+  const T* kbase = kc + g * DH + c * EPL;
+  const T* vbase = vc + g * DH + c * EPL;
+  auto row_of = [&](int i) { return ((i * S + rank) * kAttnWarps + warp) * RPW + sub; };
+  const int rows_per_iter = S * kAttnWarps * RPW;
+  const int n_iter = live ? (n_past + rows_per_iter - 1) / rows_per_iter : 0;     // the same for every warp and rank
+  uint4 kraw[kPrefetchIters][NV], vraw[kPrefetchIters][NV];
 #pragma unroll
-  for (int i = 0; i < kRowsPerIter; ++i) {
+  for (int i = 0; i < kPrefetchIters; ++i) {
     const int l = row_of(i);
-    if (i < my_blk && l < n_past) {
-      k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
-      v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) kraw[i][v] = vraw[i][v] = make_uint4(0u, 0u, 0u, 0u);   // (0 x garbage must stay 0)
+    if (i < n_iter && l < n_past) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        kraw[i][v] = ldcg_128(kbase + l * row_stride + 8 * v);
+        vraw[i][v] = ldcg_128(vbase + l * row_stride + 8 * v);
+      }
+    }
+  }
+  if (p.next_k != nullptr && live && t < 2) {
+    // rows 0 .. n_past of the next layer's caches are one contiguous range each: CTA b takes the b-th slice
+    const size_t bytes = (static_cast<size_t>(n_past) + 1) * row_stride * sizeof(T);
+    const size_t per = ((bytes + gridDim.x - 1) / gridDim.x + 127) & ~static_cast<size_t>(127);
+    const size_t off = per * blockIdx.x;
+    if (off < bytes) {
+      const size_t n = (bytes - off < per ? bytes - off : per) & ~static_cast<size_t>(15);
+      const char* src = static_cast<const char*>(t == 0 ? p.next_k : p.next_v) + off;
+      if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(n)) : "memory");
     }
   }
   float fc = 1.f, fs = 0.f;
@@ -236,84 +237,121 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
   __syncthreads();
   attn_stamp(p, 3);
 
-  // ---- every warp runs an online softmax over ITS rows (kRowsPerIter rows in flight): running max m_w,
-  //      running sum s_w and the un-normalised output acc, all in registers -- no score buffer, no block-wide
-  //      pass over the context.  Scores are rounded to T like the reference's matmul output; the
+  // ---- online softmax per row slot.  Scores are rounded to T like the reference's matmul output; the
   //      probabilities stay fp32 (the reference rounds them to T: a deviation of <= 2^-11 per weight).
   float qr[EPL];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) qr[e] = q_s[lane * EPL + e];
+  for (int e = 0; e < EPL; ++e) qr[e] = q_s[c * EPL + e];
   float m_w = -INFINITY, s_w = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  for (int i0 = 0; i0 < my_blk; i0 += kRowsPerIter) {
-    if (i0 != 0) {   // later blocks: request their rows now (the first ones are already in flight)
+  auto visit = [&](float score, const float (&vr)[EPL]) {   // one more (score, value row) for this slot
+    const float m_new = fmaxf(m_w, score);
+    const float rescale = __expf(m_w - m_new);              // exp(-inf) = 0 the first time
+    const float pl = __expf(score - m_new);
+    s_w = fmaf(s_w, rescale, pl);
 #pragma unroll
-      for (int i = 0; i < kRowsPerIter; ++i) {
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e] * rescale);
+    m_w = m_new;
+  };
+  auto group_sum = [](float d) {                            // over the LPR lanes of a row slot
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    return d;
+  };
+  for (int i0 = 0; i0 < n_iter; i0 += kPrefetchIters) {
+    if (i0 != 0) {   // later batches: request their rows now (the first ones are already in flight)
+#pragma unroll
+      for (int i = 0; i < kPrefetchIters; ++i) {
         const int l = row_of(i0 + i);
-        if (i0 + i < my_blk && l < n_past) {
-          k0raw[i] = load_raw<T, EPL>(kbase + l * row_stride, lane);
-          v0raw[i] = load_raw<T, EPL>(vbase + l * row_stride, lane);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) kraw[i][v] = vraw[i][v] = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + i < n_iter && l < n_past) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            kraw[i][v] = ldcg_128(kbase + l * row_stride + 8 * v);
+            vraw[i][v] = ldcg_128(vbase + l * row_stride + 8 * v);
+          }
         }
       }
     }
-    float sr[kRowsPerIter];
-    float mb = -INFINITY;
+    // the kPrefetchIters dot products and their shuffle chains are independent of each other and of the softmax
+    // state: no branches here, so that they overlap (a missing row scores -inf and weighs 0)
+    float sc[kPrefetchIters];
+    float m_new = m_w;
 #pragma unroll
-    for (int i = 0; i < kRowsPerIter; ++i) {
-      sr[i] = -INFINITY;
-      if (i0 + i < my_blk && row_of(i0 + i) < n_past) {   // warp-uniform
-        float kr[EPL];
-        cvt_row<T, EPL>(k0raw[i], kr);
-        float d = 0.f;
+    for (int i = 0; i < kPrefetchIters; ++i) {
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], kr[e], d);
-        sr[i] = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
-        mb = fmaxf(mb, sr[i]);
-      }
-    }
-    if (mb != -INFINITY) {
-      const float m_new = fmaxf(m_w, mb);
-      const float rescale = expf(m_w - m_new);            // exp(-inf) = 0 on the first batch
-      s_w *= rescale;
+      for (int v = 0; v < NV; ++v) {
+        const T* kh = reinterpret_cast<const T*>(&kraw[i][v]);
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) acc[e] *= rescale;
-#pragma unroll
-      for (int i = 0; i < kRowsPerIter; ++i) {
-        if (sr[i] != -INFINITY) {
-          const float pl = expf(sr[i] - m_new);
-          float vr[EPL];
-          cvt_row<T, EPL>(v0raw[i], vr);
-          s_w += pl;
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, vr[e], acc[e]);
+        for (int e = 0; e < 8; e += 2) {
+          d0 = fmaf(qr[8 * v + e], DT<T>::to_f(kh[e]), d0);
+          d1 = fmaf(qr[8 * v + e + 1], DT<T>::to_f(kh[e + 1]), d1);
         }
       }
-      m_w = m_new;
+      const float r = DT<T>::to_f(DT<T>::from_f(group_sum(d0 + d1)));
+      sc[i] = (i0 + i < n_iter && row_of(i0 + i) < n_past) ? r : -INFINITY;
+      m_new = fmaxf(m_new, sc[i]);
     }
+    const float rescale = m_new == -INFINITY ? 1.f : __expf(m_w - m_new);   // exp(-inf) = 0 the first time
+    s_w *= rescale;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] *= rescale;
+#pragma unroll
+    for (int i = 0; i < kPrefetchIters; ++i) {
+      const float pl = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - m_new);
+      s_w += pl;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const T* vh = reinterpret_cast<const T*>(&vraw[i][v]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[8 * v + e] = fmaf(pl, DT<T>::to_f(vh[e]), acc[8 * v + e]);
+      }
+    }
+    m_w = m_new;
   }
-  if (live && rank == 0 && warp == 0) {   // the new token's own key / value
+  if (live && rank == 0 && warp == 0) {   // the new token's own key / value (row slot 0 of warp 0; warp-uniform branch)
     float d = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], k_s[lane * EPL + e], d);
-    const float sn = DT<T>::to_f(DT<T>::from_f(warp_sum(d)));
-    const float m_new = fmaxf(m_w, sn);
-    const float rescale = expf(m_w - m_new);
-    const float pl = expf(sn - m_new);
-    s_w = s_w * rescale + pl;
+    for (int e = 0; e < EPL; ++e) d = fmaf(qr[e], k_s[c * EPL + e], d);
+    const float score = DT<T>::to_f(DT<T>::from_f(group_sum(d)));
+    if (sub == 0) {
+      float vr[EPL];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pl, v_s[lane * EPL + e], acc[e] * rescale);
-    m_w = m_new;
+      for (int e = 0; e < EPL; ++e) vr[e] = v_s[c * EPL + e];
+      visit(score, vr);
+    }
+  }
+  // ---- merge the row slots of the warp (neighbouring slots first): all lanes end up with the warp's state
+#pragma unroll
+  for (int o = LPR; o <= 16; o <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m_w, o);
+    const float s_o = __shfl_xor_sync(0xffffffffu, s_w, o);
+    const float M2 = fmaxf(m_w, m_o);
+    const float f_a = M2 == -INFINITY ? 0.f : __expf(m_w - M2), f_b = M2 == -INFINITY ? 0.f : __expf(m_o - M2);
+    // (the lower slot's term first in both partners: identical bits on both sides)
+    const bool low = (lane & o) == 0;
+    s_w = low ? fmaf(s_o, f_b, s_w * f_a) : fmaf(s_w, f_a, s_o * f_b);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const float a_o = __shfl_xor_sync(0xffffffffu, acc[e], o);
+      acc[e] = low ? fmaf(a_o, f_b, acc[e] * f_a) : fmaf(acc[e], f_a, a_o * f_b);
+    }
+    m_w = M2;
   }
   attn_stamp(p, 4);
 
   // ---- combine the warps (fixed order), then the cluster ranks (fixed order)
   if (lane == 0) {
     wred[warp] = m_w;
-    wred[kAttnWarps + warp] = s_w * 0.f + s_w;   // (s_w is identical in all lanes)
+    wred[kAttnWarps + warp] = s_w;
   }
+  if (sub == 0) {
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) red[warp * DH + lane * EPL + e] = acc[e];
+    for (int e = 0; e < EPL; ++e) red[warp * DH + c * EPL + e] = acc[e];
+  }
   __syncthreads();
   attn_stamp(p, 5);
   float M = -INFINITY, o = 0.f, ssum = 0.f;
@@ -323,7 +361,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) decode_attn_kernel(const Attn
 #pragma unroll
     for (int w = 0; w < kAttnWarps; ++w) {
       const float m_v = wred[w];
-      const float f = m_v == -INFINITY ? 0.f : expf(m_v - M);
+      const float f = m_v == -INFINITY ? 0.f : __expf(m_v - M);
       o = fmaf(red[w * DH + t], f, o);
       ssum = fmaf(wred[kAttnWarps + w], f, ssum);
     }
@@ -450,6 +488,15 @@ extern "C" int cgq_decode_begin_w8(const int64_t* ids, const int8_t* Wq, const v
   return CGQ_ERR_BAD_DTYPE;
 }
 
+namespace {
+thread_local const void* g_next_k = nullptr;
+thread_local const void* g_next_v = nullptr;
+}  // namespace
+extern "C" void cgq_attention_next_kv(const void* kcache_next, const void* vcache_next) {
+  g_next_k = kcache_next;
+  g_next_v = vcache_next;
+}
+
 extern "C" int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void* vcache,
                                     void* out, const int* state, int n_head, int n_groups,
                                     int d_head, int max_len, int dtype, void* stream) {
@@ -461,12 +508,13 @@ extern "C" int cgq_decode_attention(const void* qkv, const void* freqs, void* kc
   }
   if (qkv == nullptr || freqs == nullptr || kcache == nullptr || vcache == nullptr ||
       out == nullptr || state == nullptr ||
-      ((reinterpret_cast<uintptr_t>(kcache) | reinterpret_cast<uintptr_t>(vcache)) & 7)) {
+      ((reinterpret_cast<uintptr_t>(kcache) | reinterpret_cast<uintptr_t>(vcache)) & 15)) {
     set_error("cgq_decode_attention: null or misaligned pointer");
     return CGQ_ERR_MISALIGNED;
   }
   AttnParams p{qkv, freqs, kcache, vcache, out, state, n_head, n_groups, max_len, 1,
-               static_cast<unsigned long long*>(take_trace_buffer())};
+               static_cast<unsigned long long*>(take_trace_buffer()), g_next_k, g_next_v};
+  g_next_k = g_next_v = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CGQ_DTYPE_F16)
     return d_head == 128 ? launch_attn<__half, 128>(p, st) : launch_attn<__half, 64>(p, st);

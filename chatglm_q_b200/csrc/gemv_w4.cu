@@ -420,14 +420,18 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
       for (int w = 0; w < CW; ++w) tot_ss += red[w];
       const float rstd = rsqrtf(tot_ss / static_cast<float>(p.K) + p.eps);
       if (deal) {
+        // (a rolled loop on purpose: this code runs once per launch from a cold instruction cache, the second pass
+        //  should find the first one's instructions there)
+#pragma unroll 1
+        for (int i = 0; c_lo + CW * 32 * i < c_hi; ++i) {   // the band is at most the row: <= U passes
+          const int c = c_lo + tid + CW * 32 * i;
+          const bool in = c < c_hi, ld = in && c < nchunk;
+          const uint4 x = ld ? ptx::lds128(raw + (c - c_lo) * 16) : zero;
+          uint4 w = wr[0];
 #pragma unroll
-        for (int i = 0; i < U; ++i) {   // the band is at most the row: U passes cover it
-          if (c_lo + CW * 32 * i < c_hi) {
-            const int c = c_lo + tid + CW * 32 * i;
-            const bool in = c < c_hi, ld = in && c < nchunk;
-            const uint4 x = ld ? ptx::lds128(raw + (c - c_lo) * 16) : zero;
-            put(c, in, ld ? rmsnorm8<T>(x, wr[i], rstd) : zero);
-          }
+          for (int j = 1; j < U; ++j)
+            if (i == j) w = wr[j];
+          put(c, in, ld ? rmsnorm8<T>(x, w, rstd) : zero);
         }
       } else if (single) {
 #pragma unroll

@@ -95,35 +95,38 @@ __device__ __forceinline__ float sumsq8(const uint4& v) {
 }
 // RMSNorm of 8 elements, the reference's roundings: round_T(x * rstd) then round_T(. * w)
 // (chatglm_q/model.py:68-73: `_norm(x.float()).type_as(x)`, then `output * self.weight`).
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b, __half) { return h2_mul(a, b); }
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b, __nv_bfloat16) {
+  uint32_t r;
+  asm("mul.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 template <typename T>
 __device__ __forceinline__ uint4 rmsnorm8(const uint4& x, const uint4& w, float rstd) {
-  uint4 o;
+  uint4 n;
   const T* xh = reinterpret_cast<const T*>(&x);
-  const T* wh = reinterpret_cast<const T*>(&w);
-  T* oh = reinterpret_cast<T*>(&o);
+  T* nh = reinterpret_cast<T*>(&n);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const T n = DT<T>::from_f(DT<T>::to_f(xh[j]) * rstd);
-    oh[j] = DT<T>::from_f(DT<T>::to_f(n) * DT<T>::to_f(wh[j]));
-  }
-  return o;
+  for (int j = 0; j < 8; ++j) nh[j] = DT<T>::from_f(DT<T>::to_f(xh[j]) * rstd);
+  // round_T(float(n) * float(w)): the product of two 16-bit floats is exact in fp32, so the packed 16-bit multiply
+  // (one correctly rounded operation) gives the same bits
+  return make_uint4(mul2(n.x, w.x, T()), mul2(n.y, w.y, T()), mul2(n.z, w.z, T()), mul2(n.w, w.w, T()));
 }
 // SwiGLU of 8 elements: round_T(round_T(silu(h)) * gate)  (model.py:200-201, F.silu computes in fp32)
 template <typename T>
 __device__ __forceinline__ uint4 silu_gate8(const uint4& h, const uint4& g) {
-  uint4 o;
+  uint4 a;
   const T* hh = reinterpret_cast<const T*>(&h);
-  const T* gh = reinterpret_cast<const T*>(&g);
-  T* oh = reinterpret_cast<T*>(&o);
+  T* ah = reinterpret_cast<T*>(&a);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float x = DT<T>::to_f(hh[j]);
     // fast exp / divide (a few fp32 ulps from torch's expf + IEEE divide; the result is rounded to T anyway:
     // every CTA of a k-band recomputes its slice, so the accurate versions cost ~1.5 us per launch)
-    const T act = DT<T>::from_f(__fdividef(x, 1.f + __expf(-x)));
-    oh[j] = DT<T>::from_f(DT<T>::to_f(act) * DT<T>::to_f(gh[j]));
+    ah[j] = DT<T>::from_f(__fdividef(x, 1.f + __expf(-x)));
   }
-  return o;
+  // round_T(float(act) * float(gate)) == the packed 16-bit multiply (exact product, one rounding)
+  return make_uint4(mul2(a.x, g.x, T()), mul2(a.y, g.y, T()), mul2(a.z, g.z, T()), mul2(a.w, g.w, T()));
 }
 // ---- integer-MMA arithmetic of the one-token kernel (gemv_w4.cu, kImma): the activation as base-256 digits --------
 // A 32-k quantisation group of the activation row is scaled by a power of two so that its largest magnitude lands in

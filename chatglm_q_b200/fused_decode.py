@@ -285,6 +285,8 @@ class FusedDecodeModel:
             # -> o_proj stay on griddepcontrol.wait (hazards on x / qkv / ao / u: DESIGN.md §6.1a)
             self._gemv(lib, stream, layer.attn.qkv_proj, self.x, self.qkv, PRO_RMSNORM, layer.attn_ln,
                        nxt=layer.attn.o_proj, wait=prev_out if self.hand_mask & 4 else None)
+            if i + 1 < len(self.kv):     # the next layer's cache rows are requested into L2 one layer ahead
+                lib.cgq_attention_next_kv(self.kv[i + 1][0].data_ptr(), self.kv[i + 1][1].data_ptr())
             _lib.check(lib.cgq_decode_attention(
                 self.qkv.data_ptr(), self.freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.ao.data_ptr(),
                 self.state.data_ptr(), cfg.num_attention_heads, cfg.num_multi_query_groups,

@@ -100,8 +100,10 @@ class TPFusedDecodeModel(FusedDecodeModel):
             self.ids.data_ptr(), emb.weight.data_ptr(), emb.weight_scale.data_ptr(), self.x.data_ptr(),
             emb.weight.shape[0] * 2, emb.weight.shape[1], 32, self.code, self.state.data_ptr(), stream))
         idx = 0
-        for layer, sh, (kc, vc) in zip(m.layers, self._shards, self.kv):
+        for li, (layer, sh, (kc, vc)) in enumerate(zip(m.layers, self._shards, self.kv)):
             self._gemv(lib, stream, sh["qkv"], self.x, self.qkv, PRO_RMSNORM, layer.attn_ln)
+            if li + 1 < len(self.kv):
+                lib.cgq_attention_next_kv(self.kv[li + 1][0].data_ptr(), self.kv[li + 1][1].data_ptr())
             _lib.check(lib.cgq_decode_attention(
                 self.qkv.data_ptr(), self.freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.ao.data_ptr(),
                 self.state.data_ptr(), self.n_local_heads, 1, cfg.head_hidden_size, self.max_len, self.code, stream))

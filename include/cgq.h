@@ -342,6 +342,13 @@ int cgq_decode_begin_w8(const int64_t* ids, const int8_t* Wq /*[V, D]*/, const v
 int cgq_decode_attention(const void* qkv, const void* freqs, void* kcache, void* vcache, void* out,
                          const int* state, int n_head, int n_groups, int d_head, int max_len,
                          int dtype, void* stream);
+/*
+ * One-shot hint for the calling thread's NEXT cgq_decode_attention launch: the K / V caches (same layout, 16-byte
+ * aligned) the FOLLOWING attention launch of the step will read -- the next layer's.  Their live rows are requested
+ * into L2 one layer ahead (a cache row is read once per token, so it always comes from HBM, and a launch's own
+ * loads queue behind the weight requests of the neighbouring linears).  NULL cancels.  No effect on results.
+ */
+void cgq_attention_next_kv(const void* kcache_next, const void* vcache_next);
 
 /*
  * ---- Token sampling ---------------------------------------------------

@@ -252,8 +252,11 @@ int main(int argc, char** argv) {
       for (int l = 0; l < LAYERS; ++l) {
         gemv(4 * l + 0, x, qkv, CGQ_PRO_RMSNORM, nullptr);
         if (tracing && l == 1) cgq_debug_trace(atrace);
-        CG(cgq_decode_attention(qkv, freqs, kc + (size_t)l * MAXLEN * NG * DH,
-                                vc + (size_t)l * MAXLEN * NG * DH, ao, state, NH, NG, DH, MAXLEN,
+        if (l + 1 < LAYERS && !(getenv("CGQ_ATTN_PF") && atoi(getenv("CGQ_ATTN_PF")) == 0))
+          cgq_attention_next_kv(kc + (size_t)(l + 1) * MAXLEN * NG * DH, vc + (size_t)(l + 1) * MAXLEN * NG * DH);
+        const size_t kvl = (getenv("CGQ_SAME_KV") && atoi(getenv("CGQ_SAME_KV"))) ? 0 : l;   // experiment: one cache for all layers
+        CG(cgq_decode_attention(qkv, freqs, kc + kvl * MAXLEN * NG * DH,
+                                vc + kvl * MAXLEN * NG * DH, ao, state, NH, NG, DH, MAXLEN,
                                 CGQ_DTYPE_F16, st));
         gemv(4 * l + 1, ao, x, CGQ_PRO_NONE, x);
         gemv(4 * l + 2, x, u, CGQ_PRO_RMSNORM, nullptr);
@@ -376,9 +379,9 @@ int main(int argc, char** argv) {
       {
         std::vector<uint64_t> ha(kTraceWords * kTraceCtas);
         CK(cudaMemcpy(ha.data(), atrace, ha.size() * 8, cudaMemcpyDeviceToHost));
-        const char* an[8] = {"entry", "prewait", "depwait", "rope", "scores", "softmax", "exit", "-"};
+        const char* an[8] = {"entry", "prewait", "depwait", "rope", "scores", "softmax", "exit", "rows0here"};
         printf("attention of layer 1:\n");
-        for (int w = 0; w < 7; ++w) {
+        for (int w = 0; w < 8; ++w) {
           uint64_t mn = ~0ull, mx = 0; double sum = 0; int cnt = 0;
           for (int c = 0; c < kTraceCtas; ++c) {
             uint64_t v = ha[c * kTraceWords + w];
