@@ -360,7 +360,8 @@ def microbench(torch, device, peaks, seqs=(1, 128, 2048), ns=(4608, 13696, 27392
                    "GBps": round(by / us / 1e3, 1), "TFLOPs": round(fl / us / 1e6, 2),
                    "hbm_frac": round(by / us / 1e3 / peaks["hbm_gbs"], 3),
                    "tensor_frac": round(fl / us / 1e6 / peaks["bf16_tflops"], 4),
-                   "kernel": "w4_gemv_kernel (mma.sync, TMA ring, cluster DSMEM reduce)" if m <= 8
+                   "kernel": ("w4_gemv_kernel (IMMA.16832 on base-256 digits of the activation, TMA ring, cluster DSMEM reduce)"
+                              if m == 1 else "w4_gemv_kernel (mma.sync f16, TMA ring, cluster DSMEM reduce)") if m <= 8
                              else "wq_gemm_tc_kernel (tcgen05 + TMEM)"}
             if tri is not None:
                 try:

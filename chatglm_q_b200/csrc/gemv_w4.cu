@@ -980,7 +980,14 @@ int launch_t(const GemmArgs& a, int arith, const GemvFused* fu) {
   plan_bands(a.N, a.K, &SPT, &Z);
   const int grid = tiles * Z;
   // fewer CTAs than slots -> deeper rings keep the same number of bytes in flight
-  int stages = stages_env > 0 ? stages_env : (grid * 4 <= slots * 3 ? 6 : 4);
+  // Ring depth by how many CTAs of the launch share an SM: 4 -> 4 stages, 3 -> 6, <= 2 -> 8 (7 for the fused
+  // launches, whose CTAs carry the prologue buffers).  Measured on the token chain / the fused step (B200): the depth
+  // of w_out's ring (256 CTAs, 14 stages each) decides how early the neighbouring launches' CTAs fit beside it --
+  // chain 787 -> 744 us at 8, step 979 -> 953 us at 7; 9 and more lose again (profiles/r02_ring_depth.txt).
+  static const int s_small = env_int("CGQ_GEMV_STAGES_SMALL", 6, 2, 16);     // <= 3 CTAs per SM
+  static const int s_two = env_int("CGQ_GEMV_STAGES_2PERSM", 0, 0, 16);      // <= 2 CTAs per SM (0: 8 plain, 7 fused)
+  int stages = stages_env > 0 ? stages_env : (grid * 4 <= slots * 3 ? s_small : 4);
+  if (stages_env == 0 && grid * 2 <= slots) stages = s_two > 0 ? s_two : (fu != nullptr ? 7 : 8);
   const int per_cta = (SPT + Z - 1) / Z;
   if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
 

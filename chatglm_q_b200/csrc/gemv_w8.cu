@@ -591,7 +591,12 @@ int launch(const GemmArgs& a, const GemvFused* fu) {
   while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
   const int grid = tiles * Z;
   const int per_cta = (SPT + Z - 1) / Z;
-  int stages = grid * 4 <= slots * 3 ? 6 : 4;
+  // ring depth by CTAs per SM, as in gemv_w4.cu (launch_t)
+  static const int s_four = env_int("CGQ_W8_STAGES_4PERSM", 5, 2, 16);
+  static const int s_small = env_int("CGQ_W8_STAGES_SMALL", 6, 2, 16);
+  static const int s_two = env_int("CGQ_W8_STAGES_2PERSM", 0, 0, 16);
+  int stages = grid * 4 <= slots * 3 ? s_small : s_four;
+  if (s_two > 0 && grid * 2 <= slots) stages = s_two;
   if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
   CUtensorMap tmW;
   TmapKey kw{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K), KSTAGE, BN8,
