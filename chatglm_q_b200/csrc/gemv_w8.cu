@@ -630,6 +630,248 @@ int launch(const GemmArgs& a, const GemvFused* fu) {
 
 }  // namespace m1
 
+// =====================================================================================================
+// M = 2 .. 8 int8 decode kernel (round 2b) on the same skeleton: (64-column tile) x (Z k-bands) as a cluster, band
+// sums through distributed shared memory in rank order.  The activations ride in the TMA ring next to the weights:
+// two [8 tokens x 64 k] boxes with the 128-byte swizzle per stage (rows >= M are zero-filled by the tensor map), so a
+// lane's B fragment -- token g, 16 consecutive k -- is two conflict-free 16-byte loads.  Same MMA count as one
+// token (the eight MMA columns are the tokens).  Replaces the stream-K workspace kernel for bs = 2 .. 8:
+// BASELINE config 4's bs = 8 decode step 2.82 ms -> see DESIGN.md §5.0.
+namespace mx {
+
+constexpr int AX_BYTES = 2 * 8 * 128;   // activation tile of a stage
+
+struct PX {
+  const void* scale;
+  const void* bias;
+  void* C;
+  int64_t ldc;
+  int M, N, K, SPT, Z, S;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3)
+    w8_gemv_mx_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const PX p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const int S = p.S, Z = p.Z;
+  const uint32_t Wsm = base;
+  const uint32_t Asm = base + S * W_BYTES;
+  const uint32_t off_x = S * (W_BYTES + AX_BYTES);
+  float* xred = reinterpret_cast<float*>(gen + off_x);                      // [Z][8][64] band sums (used on rank 0)
+  const uint32_t xbytes = Z > 1 ? static_cast<uint32_t>(Z) * MMAX * BN8 * 4 : 0;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_x + xbytes);
+  uint64_t* empty = full + S;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;
+  const int u0 = p.SPT * z / Z, u1 = p.SPT * (z + 1) / Z;
+  const int n_units = u1 - u0;
+
+  if (threadIdx.x == CW * 32) {
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmA);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], CW);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  __syncthreads();
+  if (Z > 1) ptx::cluster_arrive_release();      // phase A: waited for before the first DSMEM store
+  ptx::pdl_launch_dependents();
+
+  if (warp == CW) {
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      const uint64_t keep = ptx::policy_evict_last();
+      auto issue_w = [&](int i, int slot) {
+        ptx::mbar_expect_tx(&full[slot], W_BYTES + AX_BYTES);
+        ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, (u0 + i) * KSTAGE, tile * BN8, &full[slot], pol);
+      };
+      auto issue_a = [&](int i, int slot) {
+        uint8_t* dst = gen + S * W_BYTES + slot * AX_BYTES;
+        ptx::tma_load_2d(dst, &tmA, (u0 + i) * KSTAGE, 0, &full[slot], keep);
+        ptx::tma_load_2d(dst + 8 * 128, &tmA, (u0 + i) * KSTAGE + 64, 0, &full[slot], keep);
+      };
+      const int prefill = min(n_units, S);
+      for (int i = 0; i < prefill; ++i) issue_w(i, i);      // weights do not depend on the previous kernel
+      ptx::pdl_wait_prior_grid();                            // the activations do
+      for (int i = 0; i < prefill; ++i) issue_a(i, i);
+      int slot = 0, phase = 1;
+      for (int i = prefill; i < n_units; ++i) {
+        ptx::mbar_wait(&empty[slot], phase ^ 1);
+        issue_w(i, slot);
+        issue_a(i, slot);
+        if (++slot == S) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+    if (Z > 1) ptx::cluster_wait_acquire();
+  } else {
+    const int g = lane >> 2, tig = lane & 3;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    int slot = 0, phase = 0;
+    for (int it = 0; it < n_units; ++it) {
+      ptx::mbar_wait(&full[slot], phase);
+      const uint32_t wa = Wsm + slot * W_BYTES + (16 * warp + g) * KSTAGE;  // row g of this warp
+      const uint32_t wb = wa + 8 * KSTAGE;                                   // row g + 8
+      // token g, k = 32 tig + 16 h .. + 15: box (tig >> 1), 16-byte chunks (4 tig + 2 h) % 8 and + 1, swizzled by g
+      const uint32_t arow = Asm + slot * AX_BYTES + (tig >> 1) * (8 * 128) + g * 128;
+      uint32_t ld_dep = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = 2 * tig + h;  // 16-byte run of the weight row: k = 16*chunk .. +15
+        const uint4 qa = ptx::lds128(wa + ((chunk ^ g) << 4));
+        const uint4 qb = ptx::lds128(wb + ((chunk ^ g) << 4));
+        const int ac = (4 * tig + 2 * h) & 7;
+        const uint4 a0 = ptx::lds128(arow + ((ac ^ g) << 4));
+        const uint4 a1 = ptx::lds128(arow + (((ac + 1) ^ g) << 4));
+        ld_dep |= qa.x | qb.x | a0.x | a1.x;
+        const uint32_t wqa[4] = {qa.x, qa.y, qa.z, qa.w};
+        const uint32_t wqb[4] = {qb.x, qb.y, qb.z, qb.w};
+        const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t fr[4];
+          Cvt8<T>::run(wqa[e], fr[0], fr[2]);
+          Cvt8<T>::run(wqb[e], fr[1], fr[3]);
+          if (e & 1)
+            ptx::mma_16816(acc2, fr, av[2 * e], av[2 * e + 1], acc2, T());
+          else
+            ptx::mma_16816(acc, fr, av[2 * e], av[2 * e + 1], acc, T());
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_after_loads(&empty[slot], ld_dep, static_cast<uint32_t>(p.K) >> 31);
+      if (++slot == S) {
+        slot = 0;
+        phase ^= 1;
+      }
+    }
+    // D fragment: tokens 2 tig, 2 tig + 1 of columns 16 w + g (acc[0], acc[1]) and 16 w + g + 8 (acc[2], acc[3])
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = acc[i] + acc2[i];
+    const int c0 = 16 * warp + g;
+    if (Z == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = 2 * tig + (i & 1), n = tile * BN8 + c0 + 8 * (i >> 1);
+        if (tok < p.M && n < p.N) {
+          const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+          static_cast<T*>(p.C)[tok * p.ldc + n] = epilogue<T>(v[i] * s, static_cast<const T*>(p.bias), n);
+        }
+      }
+    } else {
+      ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
+      const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * MMAX * BN8) * 4u, 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tok = 2 * tig + (i & 1);
+        if (tok < p.M) ptx::st_cluster_f32(remote + static_cast<uint32_t>(tok * BN8 + c0 + 8 * (i >> 1)) * 4u, v[i]);
+      }
+    }
+  }
+  if (Z > 1) {
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    if (z == 0 && threadIdx.x < BN8) {
+      const int t = threadIdx.x, n = tile * BN8 + t;
+      if (n < p.N) {
+        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+        for (int m = 0; m < p.M; ++m) {
+          float a = 0.f;
+          for (int zz = 0; zz < Z; ++zz) a += xred[(zz * MMAX + m) * BN8 + t];       // rank order: deterministic
+          static_cast<T*>(p.C)[m * p.ldc + n] = epilogue<T>(a * s, static_cast<const T*>(p.bias), n);
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch(const GemmArgs& a) {
+  static const bool pdl = env_int("CGQ_PDL", 1, 0, 1) != 0;
+  static const int s_env = env_int("CGQ_W8_MX_STAGES", 0, 0, 16);
+  const int SPT = (a.K + KSTAGE - 1) / KSTAGE;
+  const int tiles = (a.N + BN8 - 1) / BN8;
+  const int slots = 3 * sm_count();
+  int Z = 1;
+  while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
+  const int grid = tiles * Z;
+  const int per_cta = (SPT + Z - 1) / Z;
+  int stages = s_env > 0 ? s_env : (grid * 3 <= slots * 2 ? 8 : 5);
+  if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
+  CUtensorMap tmW, tmA;
+  TmapKey kw{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K), KSTAGE, BN8,
+             CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_128B};
+  int rc = get_tmap_2d(kw, &tmW);
+  if (rc != CGQ_OK) return rc;
+  TmapKey ka{a.A, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.M), static_cast<uint64_t>(a.lda) * 2, 64, 8,
+             a.dtype == CGQ_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+             CU_TENSOR_MAP_SWIZZLE_128B};
+  rc = get_tmap_2d(ka, &tmA);
+  if (rc != CGQ_OK) return rc;
+  PX prm;
+  prm.scale = a.scale;
+  prm.bias = a.bias;
+  prm.C = a.C;
+  prm.ldc = a.ldc;
+  prm.M = a.M;
+  prm.N = a.N;
+  prm.K = a.K;
+  prm.SPT = SPT;
+  prm.Z = Z;
+  prm.S = stages;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * (W_BYTES + AX_BYTES) +
+                      (Z > 1 ? static_cast<size_t>(Z) * MMAX * BN8 * 4 : 0) + 16 * stages + 32;
+  auto kern = w8_gemv_mx_kernel<T>;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  CGQ_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CGQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured[dev] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (Z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(Z);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CGQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, prm));
+  return CGQ_OK;
+}
+
+// the TMA box of the activations needs 16-byte aligned rows and a K the 64-element boxes tile exactly enough for
+// the tensor map (K % 8); anything else stays on the stream-K kernel
+bool supported(const GemmArgs& a) { return a.M >= 2 && a.M <= MMAX && a.K % 8 == 0 && (a.lda * 2) % 16 == 0; }
+
+}  // namespace mx
+
 }  // namespace
 
 bool w8_gemv_supported(const GemmArgs& a) {
@@ -643,6 +885,9 @@ int launch_w8_gemv(const GemmArgs& a) {
   static const bool legacy = env_int("CGQ_W8_STREAMK_M1", 0, 0, 1) != 0;    // the round-1 stream-K path for one token
   if (a.M == 1 && !legacy)
     return a.dtype == CGQ_DTYPE_F16 ? m1::launch<__half>(a, nullptr) : m1::launch<__nv_bfloat16>(a, nullptr);
+  static const bool legacy_mx = env_int("CGQ_W8_STREAMK_MX", 0, 0, 1) != 0; // ... and for 2 .. 8 tokens
+  if (!legacy_mx && mx::supported(a))
+    return a.dtype == CGQ_DTYPE_F16 ? mx::launch<__half>(a) : mx::launch<__nv_bfloat16>(a);
   return a.dtype == CGQ_DTYPE_F16 ? launch_t<__half>(a) : launch_t<__nv_bfloat16>(a);
 }
 

@@ -419,9 +419,9 @@ def test_install_routes_reference_backward():
     if not (ref / "chatglm_q").exists():
         pytest.skip("baseline/_ref (pip-installed reference) not present")
     sys.path.insert(0, str(ref))
-    import chatglm_q_b200
     from chatglm_q.int4 import qlinear as rq4
-    chatglm_q_b200.install("chatglm_q")
+    from chatglm_q_b200.install import install, uninstall
+    install("chatglm_q")
     try:
         k, n, m = 256, 208, 4
         a, bq, s = make_int4_case(41, m, k, n, "Q")
@@ -430,7 +430,7 @@ def test_install_routes_reference_backward():
         rq4.dynamic_quant_matmul(at, u8(bq), to_torch(s, "float16")).backward(to_torch(go, "float16"))
         assert_parity(from_torch(at.grad), orc.qmatmul_int4_grad_a(go, bq, s, "float16"), "reference autograd on cgq")
     finally:
-        chatglm_q_b200.uninstall("chatglm_q")
+        uninstall("chatglm_q")
 
 
 # ------------------------------------------------------------------ graph-captured decode step
