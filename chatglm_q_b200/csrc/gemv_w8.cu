@@ -807,7 +807,8 @@ int launch(const GemmArgs& a) {
   while (Z < 8 && tiles * (Z * 2) <= slots && SPT >= Z * 2) Z *= 2;
   const int grid = tiles * Z;
   const int per_cta = (SPT + Z - 1) / Z;
-  int stages = s_env > 0 ? s_env : (grid * 3 <= slots * 2 ? 8 : 5);
+  static const int s_big = env_int("CGQ_W8_MX_STAGES_BIG", 6, 2, 16), s_sml = env_int("CGQ_W8_MX_STAGES_SMALL", 6, 2, 16);
+  int stages = s_env > 0 ? s_env : (grid * 3 <= slots * 2 ? s_sml : s_big);
   if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
   CUtensorMap tmW, tmA;
   TmapKey kw{a.Wq, static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N), static_cast<uint64_t>(a.K), KSTAGE, BN8,
