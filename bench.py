@@ -696,15 +696,17 @@ def int8_config4(torch, device, peaks, gen_tokens=64, prompt_len=32):
         with torch.no_grad():
             fused(input_ids=ids, past_key_values=None)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(2):
+            runs = []
+            for _ in range(4):     # host-launch bound (eager reference glue): report the best and the spread
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
                 fused(input_ids=ids, past_key_values=None)
-            e1.record()
-            torch.cuda.synchronize()
-        out["prefill_2048"] = {"ms": round(e0.elapsed_time(e1) / 2, 2),
+                e1.record()
+                torch.cuda.synchronize()
+                runs.append(e0.elapsed_time(e1))
+        out["prefill_2048"] = {"ms": round(min(runs), 2), "ms_runs": [round(r, 2) for r in runs],
                                "how": "2 048-token prompt through the unmodified reference forward, int8 tcgen05 kernels behind "
-                                      "its QLinear modules (eager glue of the reference included)"}
+                                      "its QLinear modules (eager glue of the reference included); best of 4 runs"}
         del model, fused
     finally:
         uninstall("chatglm_q")

@@ -989,7 +989,8 @@ int launch_t(const GemmArgs& a, int arith, const GemvFused* fu) {
   static const int s_small = env_int("CGQ_GEMV_STAGES_SMALL", 6, 2, 16);     // <= 3 CTAs per SM
   static const int s_two = env_int("CGQ_GEMV_STAGES_2PERSM", 0, 0, 16);      // <= 2 CTAs per SM (0: 8 plain, 7 fused)
   int stages = stages_env > 0 ? stages_env : (grid * 4 <= slots * 3 ? s_small : 4);
-  if (stages_env == 0 && grid * 2 <= slots) stages = s_two > 0 ? s_two : (fu != nullptr ? 7 : 8);
+  // (one token only: the M > 1 kernel keeps 2 CTAs per SM and loses with deeper rings -- bs-8 chain 1.80 -> 2.17 ms)
+  if (stages_env == 0 && grid * 2 <= slots && a.M == 1) stages = s_two > 0 ? s_two : (fu != nullptr ? 7 : 8);
   const int per_cta = (SPT + Z - 1) / Z;
   if (stages > per_cta) stages = per_cta < 2 ? 2 : per_cta;
 
