@@ -23,6 +23,8 @@ SYMBOLS = {
                                   c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int]),
     "cgq_debug_trace": (None, [c_void_p]),
     "cgq_set_decode_arith": (c_int, [c_int]),
+    "cgq_simple_fallback_count": (ctypes.c_ulonglong, []),
+    "cgq_forbid_simple": (c_int, [c_int]),
     "cgq_attention_next_kv": (None, [c_void_p, c_void_p]),
     "cgq_w4a16_gemv_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p]),

@@ -7,6 +7,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -185,6 +187,29 @@ extern "C" size_t cgq_workspace_bytes(void) { return kWorkspaceBytes; }
 extern "C" void cgq_debug_trace(void* device_buffer) { g_trace = device_buffer; }
 extern "C" int cgq_set_decode_arith(int arith) { return default_w4_arith(arith); }
 
+// The shape-general CUDA-core kernels are a correctness net for shapes the TMA kernels cannot take (N % 16 != 0,
+// misaligned pointers, missing workspace), not a path a real layer should ever run on: AUTO counts every time it takes
+// them, and refuses when told to (CGQ_FORBID_SIMPLE=1 or cgq_forbid_simple(1)).
+namespace {
+std::atomic<unsigned long long> g_simple_auto{0};
+std::atomic<int> g_forbid_simple{[] {
+  const char* e = getenv("CGQ_FORBID_SIMPLE");
+  return (e != nullptr && atoi(e) != 0) ? 1 : 0;
+}()};
+int take_simple(const char* fn, int M, int N, int K) {
+  if (g_forbid_simple.load() != 0) {
+    set_error("%s: M=%d N=%d K=%d is not taken by the TMA / tcgen05 kernels (needs N %% 16 == 0, 16-byte aligned "
+              "pointers, lda %% 8 == 0, the workspace) and the CUDA-core kernel is forbidden (CGQ_FORBID_SIMPLE)",
+              fn, M, N, K);
+    return CGQ_ERR_BAD_SHAPE;
+  }
+  g_simple_auto.fetch_add(1);
+  return CGQ_OK;
+}
+}  // namespace
+extern "C" unsigned long long cgq_simple_fallback_count(void) { return g_simple_auto.load(); }
+extern "C" int cgq_forbid_simple(int on) { return g_forbid_simple.exchange(on != 0 ? 1 : 0); }
+
 extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, const void* scale,
                                  const void* bias, void* C, int64_t ldc, int M, int N, int K,
                                  int group, int dtype, void* workspace, size_t workspace_bytes,
@@ -206,8 +231,11 @@ extern "C" int cgq_w4a16_gemm_ex(const void* A, int64_t lda, const uint8_t* Wq, 
       impl = CGQ_IMPL_GEMV;
     else if (M > 8 && w4_tc_supported(a))
       impl = CGQ_IMPL_TC;
-    else
+    else {
+      rc = take_simple(fn, M, N, K);
+      if (rc != CGQ_OK) return rc;
       impl = CGQ_IMPL_SIMPLE;
+    }
   }
   switch (impl) {
     case CGQ_IMPL_SIMPLE:
@@ -362,8 +390,11 @@ extern "C" int cgq_w8a16_gemm_ex(const void* A, int64_t lda, const int8_t* Wq, c
       impl = CGQ_IMPL_GEMV;
     else if (M > 8 && w8_tc_supported(a))
       impl = CGQ_IMPL_TC;
-    else
+    else {
+      rc = take_simple(fn, M, N, K);
+      if (rc != CGQ_OK) return rc;
       impl = CGQ_IMPL_SIMPLE;
+    }
   }
   switch (impl) {
     case CGQ_IMPL_SIMPLE:

@@ -388,6 +388,16 @@ void cgq_debug_trace(void* device_buffer);
  */
 int cgq_set_decode_arith(int arith);
 
+/*
+ * The shape-general CUDA-core kernels (CGQ_IMPL_SIMPLE) are what cgq_w4a16_gemm / cgq_w8a16_gemm fall back to for
+ * shapes the TMA / tcgen05 kernels cannot take (N % 16 != 0, misaligned pointers, lda % 8 != 0, no workspace).  No
+ * real layer of the reference's models should run on them: cgq_simple_fallback_count() counts how often AUTO took
+ * them in this process, cgq_forbid_simple(1) (or CGQ_FORBID_SIMPLE=1) turns that into CGQ_ERR_BAD_SHAPE; returns the
+ * previous setting.
+ */
+unsigned long long cgq_simple_fallback_count(void);
+int cgq_forbid_simple(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,6 +195,37 @@ def test_int4_imma_digits_are_fp32_exact(dtype):
     assert np.isnan(run4(a2, bq, s, dtype, impl=IMPLS4["gemv_imma"])).all()
 
 
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_int4_imma_ragged_shapes(dtype):
+    """One-token integer-MMA kernel on ragged geometry: K from one quantisation group up to several k-stages with a
+    partial last stage, N from one 16-column block to ragged last tiles, bias on every other case."""
+    rng = np.random.default_rng(5)
+    for k in (32, 64, 96, 160, 384, 416, 1056):
+        for n in (16, 48, 144, 272, 400):
+            a, bq, s = make_int4_case(1000 + k + n, 1, k, n, "R", dtype)
+            bias = orc.round_to(rng.standard_normal(n) * 0.1, dtype) if (k + n) % 64 == 0 else None
+            got = run4(a, bq, s, dtype, bias=bias, impl=IMPLS4["gemv_imma"])
+            assert_parity(got, c_oracle.w4a16_gemm(a, bq, s, bias, dtype), f"imma {dtype} K={k} N={n}", rtol=rtol_for(dtype))
+
+
+@pytest.mark.parametrize("m", [2, 3, 5, 8])
+def test_int8_mx_ragged_shapes(m):
+    """w8_gemv_mx_kernel (2 .. 8 tokens, activations in the TMA ring): ragged K / N, strided activation rows, bias."""
+    rng = np.random.default_rng(6)
+    for (k, n) in [(128, 64), (136, 80), (1000, 200), (4096, 1000), (13696, 4096), (272, 4608)]:
+        a, q, s = make_int8_case(2000 + k + n + m, m, k, n, "R")
+        bias = orc.round_to(rng.standard_normal(n) * 0.1, "float16") if n % 3 == 0 else None
+        want = c_oracle.w8a16_gemm(a, q, s, bias, "float16")
+        assert_parity(run8(a, q, s, "float16", bias=bias), want, f"int8 mx M={m} K={k} N={n}")
+    # row-strided activation (lda > K): the tensor map carries the stride
+    k, n = 512, 256
+    a, q, s = make_int8_case(77, m, k, n, "Q")
+    wide = torch.zeros((m, k + 64), dtype=torch.float16, device=DEV)
+    wide[:, :k] = to_torch(a, "float16")
+    got = ops.dynamic_quant_matmul(wide[:, :k], u8(q).t(), to_torch(s, "float16"))
+    assert_parity(from_torch(got), c_oracle.w8a16_gemm(a, q, s, None, "float16"), f"int8 mx strided M={m}")
+
+
 @pytest.mark.parametrize("kind", ["Q", "R"])
 @pytest.mark.parametrize("m", [1, 3, 8])
 def test_int8_decode_shapes(kind, m):
@@ -378,6 +409,40 @@ def test_module_forward_matches_oracle():
     go = orc.round_to(np.random.default_rng(3).standard_normal((m, n)) * 0.1, "float16")
     m4.dynamic_quant_matmul(at, u8(bq), to_torch(s, "float16")).backward(to_torch(go, "float16"))
     assert_parity(from_torch(at.grad), orc.qmatmul_int4_grad_a(go, bq, s, "float16"), "int4 autograd grad_A")
+
+
+# ------------------------------------------------------------------ the CUDA-core kernels are a net, not a path
+def test_real_layer_shapes_never_take_the_simple_kernels():
+    """AUTO silently took the one-thread-per-column kernel for shapes the TMA kernels reject.  It is
+    counted now (cgq_simple_fallback_count) and can be forbidden (cgq_forbid_simple / CGQ_FORBID_SIMPLE=1): every
+    ChatGLM2-6B layer shape at every M stays on the TMA / tcgen05 kernels, an N % 16 != 0 shape is counted, and with
+    the net forbidden it raises instead of running slowly."""
+    from chatglm_q_b200 import _lib
+    lib = _lib.load()
+    before = lib.cgq_simple_fallback_count()
+    for (k, n) in [(4096, 4608), (4096, 4096), (13696, 4096), (4096, 27392), (4096, 65024)]:
+        bq = torch.randint(0, 256, (k // 2, n), dtype=torch.uint8, device=DEV)
+        s = (torch.rand((k // 32, n), device=DEV) * 0.02 - 0.01).half()
+        q8 = torch.randint(-127, 128, (n, k), dtype=torch.int8, device=DEV)
+        s8 = (torch.rand(n, device=DEV) * 0.01).half()
+        for m in (1, 3, 8, 9, 128):
+            a = torch.randn((m, k), device=DEV).half()
+            ops.dynamic_quant_matmul_s4(a, bq, s)
+            ops.dynamic_quant_matmul(a, q8.t(), s8)
+    torch.cuda.synchronize()
+    assert lib.cgq_simple_fallback_count() == before, "a real layer shape fell back to the CUDA-core kernel"
+    k, n = 512, 200                                      # N % 16 != 0: only the shape-general kernel takes it
+    a, bq, s = make_int4_case(9, 2, k, n, "Q")
+    got = run4(a, bq, s, "float16")
+    assert lib.cgq_simple_fallback_count() == before + 1
+    assert_parity(got, c_oracle.w4a16_gemm(a, bq, s, None, "float16"), "int4 N=200 on the net")
+    prev = lib.cgq_forbid_simple(1)
+    try:
+        with pytest.raises(RuntimeError, match="CGQ_FORBID_SIMPLE"):
+            run4(a, bq, s, "float16")
+        run4(a, bq, s, "float16", impl=ops.IMPL_SIMPLE)   # naming the kernel explicitly is still allowed
+    finally:
+        lib.cgq_forbid_simple(prev)
 
 
 # ------------------------------------------------------------------ backward (SURVEY §8f rank 4)
