@@ -707,6 +707,36 @@ def int8_config4(torch, device, peaks, gen_tokens=64, prompt_len=32):
         out["prefill_2048"] = {"ms": round(min(runs), 2), "ms_runs": [round(r, 2) for r in runs],
                                "how": "2 048-token prompt through the unmodified reference forward, int8 tcgen05 kernels behind "
                                       "its QLinear modules (eager glue of the reference included); best of 4 runs"}
+        # decode at bs = 8 end to end: `generate` is batch-1 only (decoder.py:70), so the reference's own
+        # model.forward(input_ids [8, L], past_key_values) is driven greedily -- unmodified eager forward (its torch.cat
+        # KV growth, its attention), the int8 linears on cgq_w8a16_gemm at M = 8 (w8_gemv_mx_kernel)
+        from chatglm_q_b200.graph_decode import GraphDecodeModel
+        bs, steps8 = 8, 24
+        pin_in = torch.empty((bs, 1), dtype=torch.int64).pin_memory()
+        pin_out = torch.empty((bs,), dtype=torch.int64).pin_memory()
+        prompt8 = torch.randint(1000, 60000, (bs, prompt_len), generator=torch.Generator().manual_seed(1)).to(device)
+        for name, m8, how in (
+                ("decode_bs8_e2e", GraphDecodeModel(model, max_len=prompt_len + steps8 + 16),
+                 "reference model.forward at batch 8 captured in ONE CUDA graph per step (chatglm_q_b200.GraphDecodeModel: "
+                 "static 8-row KV window, the reference's own attention / norms inside the graph), int8 linears on "
+                 "cgq_w8a16_gemm at M = 8 (w8_gemv_mx_kernel)"),
+                ("decode_bs8_e2e_eager", model,
+                 "unmodified reference model.forward at batch 8, eager (its torch.cat KV growth), int8 linears on "
+                 "cgq_w8a16_gemm at M = 8")):
+            with torch.no_grad():
+                _, lg, kv = m8(input_ids=prompt8, past_key_values=None)
+                tok = lg[:, -1].argmax(-1)
+                lat = []
+                for i in range(steps8 + 4):
+                    t0 = time.perf_counter()
+                    pin_in[:, 0] = pin_out if i else tok.cpu()
+                    ids8 = pin_in.to(device, non_blocking=True)                  # H2D: this step's 8 token ids
+                    _, lg, kv = m8(input_ids=ids8, past_key_values=kv)
+                    pin_out.copy_(lg[:, -1].argmax(-1), non_blocking=False)      # D2H: the 8 sampled tokens (greedy)
+                    lat.append(time.perf_counter() - t0)
+            lat = lat[4:]
+            out[name] = {"tok_s": round(bs * len(lat) / sum(lat), 1), "ms_per_step": round(1e3 * sum(lat) / len(lat), 3),
+                         "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 64, "steps": len(lat), "how": how}
         del model, fused
     finally:
         uninstall("chatglm_q")

@@ -38,7 +38,8 @@ class GraphDecodeModel:
         self.max_len = int(max_len)
         self.graph: torch.cuda.CUDAGraph | None = None
         self.n_valid = 0
-        self._eager_kv = None      # set when the window is exhausted / the batch is > 1: plain reference path
+        self.batch = 1             # rows of the static window (a batch is captured too, on CUDA)
+        self._eager_kv = None      # set when the window is exhausted (or a CPU batch): plain reference path
         self._epoch = 0
 
     # nn.Module-ish surface the decoder / loader touch
@@ -87,7 +88,7 @@ class GraphDecodeModel:
             return self.model(input_ids=input_ids, past_key_values=past_key_values, **kwargs)
         fresh = (past_key_values is None or not isinstance(past_key_values, _GraphCache)
                  or past_key_values.owner is not self or past_key_values.epoch != self._epoch)
-        if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != 1:
+        if fresh or input_ids.shape[1] != 1 or input_ids.shape[0] != self.batch:
             # prefill through the unmodified model, then move its cache into the static window
             if fresh:
                 self._epoch += 1
@@ -114,19 +115,22 @@ class GraphDecodeModel:
         n = kv[0][0].shape[1]
         L = self.max_len - 1
         self._eager_kv = None
-        if n > L or kv[0][0].shape[0] != 1:      # longer than the window, or a batch: the static buffers hold one row
+        B = kv[0][0].shape[0]
+        if n > L or (B != 1 and not kv[0][0].is_cuda):   # longer than the window (or a batch without a GPU to capture on)
             self._eager_kv = kv
             self.n_valid = n
+            self.batch = 1
             return
         first = not hasattr(self, "kv") or self.kv[0][0].device != kv[0][0].device \
-            or self.kv[0][0].dtype != kv[0][0].dtype
+            or self.kv[0][0].dtype != kv[0][0].dtype or self.kv[0][0].shape[0] != B
         if first:
-            self.kv = tuple((torch.zeros((1, L, *k.shape[2:]), device=k.device, dtype=k.dtype),
-                             torch.zeros((1, L, *v.shape[2:]), device=v.device, dtype=v.dtype)) for k, v in kv)
-            self.mask = torch.zeros((1, self.max_len), dtype=torch.long, device=device)
-            self.ids = torch.zeros((1, 1), dtype=torch.long, device=device)
-            self.logits = torch.zeros((1, 1, logits.shape[-1]), device=device, dtype=logits.dtype)
+            self.kv = tuple((torch.zeros((B, L, *k.shape[2:]), device=k.device, dtype=k.dtype),
+                             torch.zeros((B, L, *v.shape[2:]), device=v.device, dtype=v.dtype)) for k, v in kv)
+            self.mask = torch.zeros((B, self.max_len), dtype=torch.long, device=device)
+            self.ids = torch.zeros((B, 1), dtype=torch.long, device=device)
+            self.logits = torch.zeros((B, 1, logits.shape[-1]), device=device, dtype=logits.dtype)
             self.graph = None
+        self.batch = B
         for (ks, vs), (k, v) in zip(self.kv, kv):
             ks.zero_()
             vs.zero_()

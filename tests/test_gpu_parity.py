@@ -499,9 +499,11 @@ def test_install_routes_reference_backward():
 
 
 # ------------------------------------------------------------------ graph-captured decode step
-def test_graph_decode_matches_eager_reference():
+@pytest.mark.parametrize("batch", [1, 4])
+def test_graph_decode_matches_eager_reference(batch):
     """The CUDA-graph wrapper must reproduce the unmodified reference model token by token (greedy),
-    driven by the unmodified reference decoder loop contract: model(input_ids=, past_key_values=)."""
+    driven by the unmodified reference decoder loop contract: model(input_ids=, past_key_values=); batch 4 is
+    BASELINE config 4's `model.forward(input_ids [B, L])` decode (a static window of B rows, M = B linears)."""
     import sys
     from pathlib import Path
     ref = Path(__file__).resolve().parent.parent / "baseline" / "_ref"
@@ -532,22 +534,24 @@ def test_graph_decode_matches_eager_reference():
                     mod.weight.copy_(torch.randint(0, 256, mod.weight.shape, dtype=torch.uint8, device=DEV, generator=g))
                     mod.weight_scale.copy_((torch.rand(mod.weight_scale.shape, device=DEV, generator=g) * 0.2 + 0.05).half())
         model.eval()
-        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000]], device=DEV)
+        prompt = torch.tensor([[5, 17, 300, 42, 7, 99, 1000], [8, 1, 2, 3, 4, 5, 6], [900, 800, 700, 600, 500, 400, 300],
+                               [11, 12, 13, 14, 15, 16, 17]][:batch], device=DEV)
         wrapped = GraphDecodeModel(model, max_len=64)
         with torch.no_grad():
             _, lg_e, kv_e = model(input_ids=prompt)
             _, lg_g, kv_g = wrapped(input_ids=prompt, past_key_values=None)
             assert torch.equal(lg_e, lg_g)
-            tok = lg_e[0, -1].argmax().reshape(1, 1)
+            tok = lg_e[:, -1].argmax(-1).reshape(batch, 1)
             for step in range(20):
                 _, lg_e, kv_e = model(input_ids=tok, past_key_values=kv_e)
                 _, lg_g, kv_g = wrapped(input_ids=tok, past_key_values=kv_g)
-                a, b = lg_e[0, -1].float(), lg_g[0, -1].float()
+                assert wrapped.graph is not None and wrapped._eager_kv is None, "the step must be a graph replay"
+                a, b = lg_e[:, -1].float(), lg_g[:, -1].float()
                 assert torch.isfinite(b).all()
                 err = (a - b).abs().max().item()
                 assert err <= 2e-2 * a.abs().max().item() + 1e-3, f"step {step}: logits differ by {err}"
-                assert a.argmax().item() == b.argmax().item(), f"step {step}: greedy token differs"
-                tok = a.argmax().reshape(1, 1)
+                assert torch.equal(a.argmax(-1), b.argmax(-1)), f"step {step}: greedy token differs"
+                tok = a.argmax(-1).reshape(batch, 1)
     finally:
         uninstall("chatglm_q")
 
