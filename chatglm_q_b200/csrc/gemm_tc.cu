@@ -241,6 +241,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       int s = 0, ph = 0, ab = 0, aph = 0, acc = 0, cph = 0;
+      // The issuer is ONE thread: everything it executes per stage is serial latency in front of the tensor pipe (the
+      // per-stage descriptor construction -- eight 64-bit shift / mask chains -- was what paced the pipeline at ~780
+      // cycles per 64-k stage whatever the token block).  Descriptors are built once; a stage adds its offset to the
+      // 14-bit start-address field (shared memory is < 256 KB: the field cannot carry).
+      // int4 A: MN-major, 64-column halves 8 KB apart (LBO), 8-k atoms 1 KB apart (SBO); K-step = 2 atoms
+      // int8 A: K-major rows of 128 B like B; B: K-major rows of 128 B, 8-row atoms 1 KB apart; K-step = 32 B
+      const uint64_t adesc0 = kW8 ? make_desc(base, 16, ATOM) : make_desc(base, (BK / 8) * ATOM, ATOM);
+      const uint64_t bdesc0 = make_desc(base + off_stage, 16, ATOM);
+      constexpr uint32_t a_kstep = kW8 ? (32u >> 4) : ((2u * ATOM) >> 4);
+      const uint32_t b_stage = stage_bytes >> 4;
       for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
         const int sp = item % p.k_splits;
         const int ks0 = p.k_stages * sp / p.k_splits, ks1 = p.k_stages * (sp + 1) / p.k_splits;
@@ -251,17 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           ptx::mbar_wait(&full_tma[s], ph);
           ptx::mbar_wait(&a_full[ab], aph);
           ptx::tc_fence_after();
-          const uint32_t a_addr = base + ab * A_BYTES;
-          const uint32_t b_addr = base + off_stage + s * stage_bytes;
+          const uint64_t adesc = adesc0 + static_cast<uint32_t>(ab) * (static_cast<uint32_t>(A_BYTES) >> 4);
+          const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(s) * b_stage;
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            // int4 A: MN-major, 64-column halves 8 KB apart (LBO), 8-k atoms 1 KB apart (SBO)
-            // int8 A: K-major rows of 128 B like B
-            const uint64_t adesc = kW8 ? make_desc(a_addr + k4 * 32, 16, ATOM)
-                                       : make_desc(a_addr + k4 * 2 * ATOM, (BK / 8) * ATOM, ATOM);
-            // B: K-major rows of 128 B, 8-row atoms 1 KB apart; K-step = 32 B inside the row
-            const uint64_t bdesc = make_desc(b_addr + k4 * 32, 16, ATOM);
-            ptx::umma_f16_ss(d_tmem, adesc, bdesc, p.idesc, (ks != ks0 || k4 != 0) ? 1u : 0u);
+          for (int k4 = 0; k4 < BK / 16; ++k4)
+            ptx::umma_f16_ss(d_tmem, adesc + k4 * a_kstep, bdesc + k4 * 2u, p.idesc, (ks != ks0 || k4 != 0) ? 1u : 0u);
+          {
           }
           ptx::umma_commit(&empty_tma[s]);   // stage (activations + packed) reusable when MMAs retire
           ptx::umma_commit(&a_empty[ab]);
