@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == kTmaWarp) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    {   // every lane runs the loop, lane 0 issues (see the MMA issuer below)
+      const uint32_t issue = lane == 0 ? 1u : 0u;
       const uint64_t pol_w = ptx::policy_evict_first();   // weights: streamed (re-use is in L2 window)
       const uint64_t pol_a = ptx::policy_evict_last();    // activations: re-read by every n-tile
       int s = 0, ph = 0;
@@ -221,14 +222,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int ks0 = p.k_stages * sp / p.k_splits, ks1 = p.k_stages * (sp + 1) / p.k_splits;
         for (int ks = ks0; ks < ks1; ++ks) {
           ptx::mbar_wait(&empty_tma[s], ph ^ 1);
-          uint8_t* st = gen + off_stage + s * stage_bytes;
-          ptx::mbar_expect_tx(&full_tma[s], b_bytes + (kW8 ? P8_BYTES : P_BYTES + S_BYTES));
-          ptx::tma_load_2d(st, &tmA, ks * BK, mb * MB, &full_tma[s], pol_a);
+          const uint32_t st = base + off_stage + s * stage_bytes;
+          ptx::mbar_expect_tx_warp(&full_tma[s], b_bytes + (kW8 ? P8_BYTES : P_BYTES + S_BYTES), issue);
+          ptx::tma_load_2d_warp(st, &tmA, ks * BK, mb * MB, &full_tma[s], pol_a, issue);
           if (kW8) {
-            ptx::tma_load_2d(st + b_bytes, &tmP, ks * BK, nt * TN, &full_tma[s], pol_w);
+            ptx::tma_load_2d_warp(st + b_bytes, &tmP, ks * BK, nt * TN, &full_tma[s], pol_w, issue);
           } else {
-            ptx::tma_load_2d(st + b_bytes, &tmP, nt * TN, ks * (BK / 2), &full_tma[s], pol_w);
-            ptx::tma_load_2d(st + b_bytes + P_BYTES, &tmS, nt * TN, ks * (BK / 32), &full_tma[s], pol_w);
+            ptx::tma_load_2d_warp(st + b_bytes, &tmP, nt * TN, ks * (BK / 2), &full_tma[s], pol_w, issue);
+            ptx::tma_load_2d_warp(st + b_bytes + P_BYTES, &tmS, nt * TN, ks * (BK / 32), &full_tma[s], pol_w, issue);
           }
           if (++s == STAGES) {
             s = 0;
@@ -239,7 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // EVERY lane of the warp runs this loop (converged), lane 0 issues (predicate inside the asm): inside a divergent
+    // `if (lane == 0)` region the compiler wraps each tcgen05 instruction in an ELECT / R2UR / BRA.U.ANY waterfall
+    // loop -- ~75 dependent instructions per stage for the single issuing thread (tools/umma_rate.cu: 1005 -> 509
+    // cycles per stage of four m128 k16 MMAs + commit, i.e. the 4 x 127 cycles the MMAs take whatever their N).
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;
       int s = 0, ph = 0, ab = 0, aph = 0, acc = 0, cph = 0;
       // The issuer is ONE thread: everything it executes per stage is serial latency in front of the tensor pipe (the
       // per-stage descriptor construction -- eight 64-bit shift / mask chains -- was what paced the pipeline at ~780
@@ -265,11 +271,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(s) * b_stage;
 #pragma unroll
           for (int k4 = 0; k4 < BK / 16; ++k4)
-            ptx::umma_f16_ss(d_tmem, adesc + k4 * a_kstep, bdesc + k4 * 2u, p.idesc, (ks != ks0 || k4 != 0) ? 1u : 0u);
+            ptx::umma_f16_ss_warp(d_tmem, adesc + k4 * a_kstep, bdesc + k4 * 2u, p.idesc, (ks != ks0 || k4 != 0) ? 1u : 0u,
+                                  issue);
           {
           }
-          ptx::umma_commit(&empty_tma[s]);   // stage (activations + packed) reusable when MMAs retire
-          ptx::umma_commit(&a_empty[ab]);
+          ptx::umma_commit_warp(&empty_tma[s], issue);   // stage (activations + packed) reusable when MMAs retire
+          ptx::umma_commit_warp(&a_empty[ab], issue);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             aph ^= 1;
           }
         }
-        ptx::umma_commit(&acc_full[acc]);
+        ptx::umma_commit_warp(&acc_full[acc], issue);
         if (++acc == 2) {
           acc = 0;
           cph ^= 1;

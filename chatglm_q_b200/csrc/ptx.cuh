@@ -95,6 +95,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// The same two, executed by every lane of a converged warp and issued by the lanes whose `issue` is non-zero: see
+// umma_f16_ss_warp (a divergent single-lane region costs an ELECT / BRA.U.ANY waterfall per uniform-datapath
+// instruction, and the producer's THROUGHPUT bounds the pipeline however deep the ring is).
+__device__ __forceinline__ void mbar_expect_tx_warp(uint64_t* bar, uint32_t bytes, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_warp(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;\n\t}" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy), "r"(issue)
+      : "memory");
+}
 // 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16).
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes,
                                              uint64_t* bar) {
@@ -304,6 +325,28 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same, executed by EVERY lane of a converged warp and issued by the lanes whose `issue` is non-zero (lane 0): in
+// a divergent `if (lane == 0)` region the compiler wraps each tcgen05 instruction (uniform-register operands) in an
+// ELECT / R2UR / BRA.U.ANY waterfall loop, ~20 instructions of dependent predicate latency per MMA for the single
+// issuing thread -- measured 770 cycles per 4 MMAs + commit whatever their shape (tools/umma_rate.cu).
+__device__ __forceinline__ void umma_f16_ss_warp(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
       : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]
