@@ -320,26 +320,29 @@ __global__ void __launch_bounds__(kThreads, kM1 ? 4 : 2)
   ptx::pdl_launch_dependents();
 
   if (warp == CW) {
-    // =========================== producer: one lane drives TMA ===========================
-    if (lane == 0) {
-      stamp(p, 1);
+    // =========================== producer: lane 0 drives TMA ===========================
+    // (every lane runs the loop, the issue is predicated on lane 0 inside the asm: a divergent single-lane region
+    //  costs an ELECT / BRA.U.ANY waterfall per TMA / mbarrier instruction -- see ptx::tma_load_2d_warp)
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;
+      if (lane == 0) stamp(p, 1);
       const uint64_t pol = ptx::policy_evict_first();
       auto issue_w = [&](int i, int slot) {
         const int ks = u0 + i;
-        ptx::mbar_expect_tx(&full[slot], W_BYTES + S_BYTES);
-        ptx::tma_load_2d(gen + slot * W_BYTES, &tmW, tile * BN, ks * ROWS, &full[slot], pol);
-        ptx::tma_load_2d(gen + S * W_BYTES + slot * S_BYTES, &tmS, tile * BN, ks * CW, &full[slot],
-                         pol);
+        ptx::mbar_expect_tx_warp(&full[slot], W_BYTES + S_BYTES, issue);
+        ptx::tma_load_2d_warp(Wsm + slot * W_BYTES, &tmW, tile * BN, ks * ROWS, &full[slot], pol, issue);
+        ptx::tma_load_2d_warp(Ssm + slot * S_BYTES, &tmS, tile * BN, ks * CW, &full[slot], pol, issue);
       };
       const int prefill = min(n_units, S);
       // weights do not depend on the previous kernel: start streaming them before the PDL wait
       for (int i = 0; i < prefill; ++i) issue_w(i, i);
-      // next launch's weights -> L2, spread over this CTA's refill iterations (own loads first)
+      // next launch's weights -> L2, spread over this CTA's refill iterations (own loads first; off unless CGQ_PF_MB)
       int pf_next = blockIdx.x;
       const int pf_mine = p.pf_pieces > 0 ? (p.pf_pieces - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const int pf_iters = n_units - prefill;
       const int pf_per = pf_iters > 0 ? (pf_mine + pf_iters - 1) / pf_iters : pf_mine;
       auto pf_issue = [&](int count) {
+        if (lane != 0) return;
         for (int c = 0; c < count && pf_next < p.pf_pieces; ++c, pf_next += gridDim.x)
           prefetch_piece(p, pf_next);
       };
