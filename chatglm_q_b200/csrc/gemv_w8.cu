@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(kThreads, 4)
   float* sred = xred + 8 * BN8;                                             // [CW] sum(x^2) partials
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_x + 8 * BN8 * 4 + 64);
   uint64_t* empty = full + S;
-  const uint32_t Aband = base + ((off_x + 8 * BN8 * 4 + 64 + 16 * S + 15) & ~15u);
+  uint64_t* xbar = empty + S;   // rank 0: completes when the band sums of ranks 1 .. Z-1 have landed in xred
+  const uint32_t Aband = base + ((off_x + 8 * BN8 * 4 + 64 + 16 * S + 16 + 15) & ~15u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;
@@ -395,6 +396,10 @@ __global__ void __launch_bounds__(kThreads, 4)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], CW);
+    }
+    if (Z > 1 && z == 0) {     // the remote st.async stores carry the arrival: two columns per consumer quad
+      ptx::mbar_init(xbar, 1);
+      ptx::mbar_expect_tx(xbar, static_cast<uint32_t>(Z - 1) * BN8 * 4u);
     }
     ptx::fence_mbar_init();
   }
@@ -518,26 +523,33 @@ __global__ void __launch_bounds__(kThreads, 4)
         finish(v1, c1);
       }
     } else {
+      // band sums meet in rank 0's shared memory: ranks 1 .. Z-1 push theirs with st.async onto rank 0's mbarrier (the
+      // data is its own arrival signal: no closing cluster barrier, the pushing CTAs exit at once), as gemv_w4.cu does
       ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
-      if (tig == 0) {
-        const uint32_t local = ptx::smem_u32(xred) + static_cast<uint32_t>(z * BN8) * 4u;
-        const uint32_t remote = ptx::mapa_rank(local, 0);
-        ptx::st_cluster_f32(remote + c0 * 4, v0);
-        ptx::st_cluster_f32(remote + c1 * 4, v1);
-      }
-    }
-  }
-  if (Z > 1) {
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-    if (z == 0 && threadIdx.x < BN8) {
-      const int t = threadIdx.x, n = tile * BN8 + t;
-      if (n < p.N) {
-        float acc = 0.f;
-        for (int zz = 0; zz < Z; ++zz) acc += xred[zz * BN8 + t];       // rank order: deterministic
-        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-        static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(acc * s, static_cast<const T*>(p.bias), n),
-                                                   static_cast<const T*>(p.resid), n);
+      if (z != 0) {
+        if (tig == 0) {
+          const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * BN8) * 4u, 0);
+          const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
+          ptx::st_async_cluster_f32(remote + c0 * 4, v0, rbar);
+          ptx::st_async_cluster_f32(remote + c1 * 4, v1, rbar);
+        }
+      } else {
+        if (tig == 0) {
+          xred[c0] = v0;
+          xred[c1] = v1;
+        }
+        ptx::named_bar_sync(1, CW * 32);
+        if (threadIdx.x < BN8) {
+          ptx::mbar_wait(xbar, 0);
+          const int t = threadIdx.x, n = tile * BN8 + t;
+          if (n < p.N) {
+            float acc = 0.f;
+            for (int zz = 0; zz < Z; ++zz) acc += xred[zz * BN8 + t];       // rank order: deterministic
+            const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+            static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(acc * s, static_cast<const T*>(p.bias), n),
+                                                       static_cast<const T*>(p.resid), n);
+          }
+        }
       }
     }
   }
@@ -545,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 
 template <typename T, int kPro>
 int launch_pro(const GemmArgs& a, const CUtensorMap& tmW, const P1& prm, int grid, bool pdl) {
-  const size_t smem = 1024 + static_cast<size_t>(prm.S) * W_BYTES + 8 * BN8 * 4 + 64 + 16 * prm.S + 32 +
+  const size_t smem = 1024 + static_cast<size_t>(prm.S) * W_BYTES + 8 * BN8 * 4 + 64 + 16 * prm.S + 48 +
                       static_cast<size_t>(prm.band_units) * KSTAGE * 2;
   auto kern = w8_gemv_m1_kernel<T, kPro>;
   static size_t configured[64] = {0};
@@ -663,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 3)
   const uint32_t xbytes = Z > 1 ? static_cast<uint32_t>(Z) * MMAX * BN8 * 4 : 0;
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_x + xbytes);
   uint64_t* empty = full + S;
+  uint64_t* xbar = empty + S;   // rank 0: completes when the band sums of ranks 1 .. Z-1 have landed in xred
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / Z, z = blockIdx.x - tile * Z;
@@ -675,6 +688,10 @@ __global__ void __launch_bounds__(kThreads, 3)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], CW);
+    }
+    if (Z > 1 && z == 0) {
+      ptx::mbar_init(xbar, 1);
+      ptx::mbar_expect_tx(xbar, static_cast<uint32_t>(Z - 1) * static_cast<uint32_t>(p.M) * BN8 * 4u);
     }
     ptx::fence_mbar_init();
   }
@@ -770,26 +787,35 @@ __global__ void __launch_bounds__(kThreads, 3)
         }
       }
     } else {
+      // ranks 1 .. Z-1 push their band sums with st.async onto rank 0's mbarrier and exit; rank 0 adds in rank order
       ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
-      const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * MMAX * BN8) * 4u, 0);
+      if (z != 0) {
+        const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * MMAX * BN8) * 4u, 0);
+        const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int tok = 2 * tig + (i & 1);
-        if (tok < p.M) ptx::st_cluster_f32(remote + static_cast<uint32_t>(tok * BN8 + c0 + 8 * (i >> 1)) * 4u, v[i]);
-      }
-    }
-  }
-  if (Z > 1) {
-    ptx::cluster_arrive_release();
-    ptx::cluster_wait_acquire();
-    if (z == 0 && threadIdx.x < BN8) {
-      const int t = threadIdx.x, n = tile * BN8 + t;
-      if (n < p.N) {
-        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-        for (int m = 0; m < p.M; ++m) {
-          float a = 0.f;
-          for (int zz = 0; zz < Z; ++zz) a += xred[(zz * MMAX + m) * BN8 + t];       // rank order: deterministic
-          static_cast<T*>(p.C)[m * p.ldc + n] = epilogue<T>(a * s, static_cast<const T*>(p.bias), n);
+        for (int i = 0; i < 4; ++i) {
+          const int tok = 2 * tig + (i & 1);
+          if (tok < p.M)
+            ptx::st_async_cluster_f32(remote + static_cast<uint32_t>(tok * BN8 + c0 + 8 * (i >> 1)) * 4u, v[i], rbar);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tok = 2 * tig + (i & 1);
+          if (tok < p.M) xred[tok * BN8 + c0 + 8 * (i >> 1)] = v[i];
+        }
+        ptx::named_bar_sync(1, CW * 32);
+        if (threadIdx.x < BN8) {
+          ptx::mbar_wait(xbar, 0);
+          const int t = threadIdx.x, n = tile * BN8 + t;
+          if (n < p.N) {
+            const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+            for (int m = 0; m < p.M; ++m) {
+              float a = 0.f;
+              for (int zz = 0; zz < Z; ++zz) a += xred[(zz * MMAX + m) * BN8 + t];       // rank order: deterministic
+              static_cast<T*>(p.C)[m * p.ldc + n] = epilogue<T>(a * s, static_cast<const T*>(p.bias), n);
+            }
+          }
         }
       }
     }
@@ -832,7 +858,7 @@ int launch(const GemmArgs& a) {
   prm.Z = Z;
   prm.S = stages;
   const size_t smem = 1024 + static_cast<size_t>(stages) * (W_BYTES + AX_BYTES) +
-                      (Z > 1 ? static_cast<size_t>(Z) * MMAX * BN8 * 4 : 0) + 16 * stages + 32;
+                      (Z > 1 ? static_cast<size_t>(Z) * MMAX * BN8 * 4 : 0) + 16 * stages + 48;
   auto kern = w8_gemv_mx_kernel<T>;
   static size_t configured[64] = {0};
   int dev = 0;
