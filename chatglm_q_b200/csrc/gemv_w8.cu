@@ -462,6 +462,16 @@ __global__ void __launch_bounds__(kThreads, 4)
         ptx::sts128(Aband + (c - c_lo) * 16, v);
       }
     }
+    // scale / bias / residual of the column this thread will store (threads 0 .. 63 of the rank that stores), requested
+    // now: the tail of a 4 us launch should not wait for three more L2 round trips
+    float pre_s = 0.f;
+    T pre_b = DT<T>::from_f(0.f), pre_r = DT<T>::from_f(0.f);
+    if ((Z == 1 || z == 0) && threadIdx.x < BN8 && tile * BN8 + static_cast<int>(threadIdx.x) < p.N) {
+      const int n = tile * BN8 + threadIdx.x;
+      pre_s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+      if (p.bias != nullptr) pre_b = static_cast<const T*>(p.bias)[n];
+      if (p.resid != nullptr) pre_r = w4::ldcg_t<T>(static_cast<const T*>(p.resid) + n);
+    }
     ptx::named_bar_sync(1, CW * 32);
 
     const int g = lane >> 2, tig = lane & 3;
@@ -509,46 +519,33 @@ __global__ void __launch_bounds__(kThreads, 4)
     // D fragment, token 0 (lanes tig == 0): acc[0] = column 16 w + g, acc[2] = column 16 w + g + 8
     const float v0 = acc[0] + acc2[0], v1 = acc[2] + acc2[2];
     const int c0 = 16 * warp + g, c1 = c0 + 8;
-    auto finish = [&](float v, int col) {
-      const int n = tile * BN8 + col;
-      if (n < p.N) {
-        const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-        static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(v * s, static_cast<const T*>(p.bias), n),
-                                                   static_cast<const T*>(p.resid), n);
-      }
-    };
-    if (Z == 1) {
-      if (tig == 0) {
-        finish(v0, c0);
-        finish(v1, c1);
-      }
-    } else {
+    if (Z > 1) ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
+    if (Z > 1 && z != 0) {
       // band sums meet in rank 0's shared memory: ranks 1 .. Z-1 push theirs with st.async onto rank 0's mbarrier (the
       // data is its own arrival signal: no closing cluster barrier, the pushing CTAs exit at once), as gemv_w4.cu does
-      ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
-      if (z != 0) {
-        if (tig == 0) {
-          const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * BN8) * 4u, 0);
-          const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
-          ptx::st_async_cluster_f32(remote + c0 * 4, v0, rbar);
-          ptx::st_async_cluster_f32(remote + c1 * 4, v1, rbar);
-        }
-      } else {
-        if (tig == 0) {
-          xred[c0] = v0;
-          xred[c1] = v1;
-        }
-        ptx::named_bar_sync(1, CW * 32);
-        if (threadIdx.x < BN8) {
-          ptx::mbar_wait(xbar, 0);
-          const int t = threadIdx.x, n = tile * BN8 + t;
-          if (n < p.N) {
-            float acc = 0.f;
-            for (int zz = 0; zz < Z; ++zz) acc += xred[zz * BN8 + t];       // rank order: deterministic
-            const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-            static_cast<T*>(p.C)[n] = w4::add_resid<T>(epilogue<T>(acc * s, static_cast<const T*>(p.bias), n),
-                                                       static_cast<const T*>(p.resid), n);
-          }
+      if (tig == 0) {
+        const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * BN8) * 4u, 0);
+        const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
+        ptx::st_async_cluster_f32(remote + c0 * 4, v0, rbar);
+        ptx::st_async_cluster_f32(remote + c1 * 4, v1, rbar);
+      }
+    } else {
+      if (tig == 0) {
+        xred[c0] = v0;
+        xred[c1] = v1;
+      }
+      ptx::named_bar_sync(1, CW * 32);
+      if (threadIdx.x < BN8) {
+        if (Z > 1) ptx::mbar_wait(xbar, 0);
+        const int t = threadIdx.x, n = tile * BN8 + t;
+        if (n < p.N) {
+          float acc = 0.f;
+          for (int zz = 0; zz < Z; ++zz) acc += xred[zz * BN8 + t];       // rank order: deterministic
+          // round(acc * scale) -> (+ bias, rounded) -> (+ residual, rounded), on the values requested after staging
+          T val = DT<T>::from_f(acc * pre_s);
+          if (p.bias != nullptr) val = DT<T>::from_f(DT<T>::to_f(val) + DT<T>::to_f(pre_b));
+          if (p.resid != nullptr) val = DT<T>::from_f(DT<T>::to_f(pre_r) + DT<T>::to_f(val));
+          static_cast<T*>(p.C)[n] = val;
         }
       }
     }
@@ -672,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 3)
   const uint32_t Asm = base + S * W_BYTES;
   const uint32_t off_x = S * (W_BYTES + AX_BYTES);
   float* xred = reinterpret_cast<float*>(gen + off_x);                      // [Z][8][64] band sums (used on rank 0)
-  const uint32_t xbytes = Z > 1 ? static_cast<uint32_t>(Z) * MMAX * BN8 * 4 : 0;
+  const uint32_t xbytes = static_cast<uint32_t>(Z) * MMAX * BN8 * 4;
   uint64_t* full = reinterpret_cast<uint64_t*>(gen + off_x + xbytes);
   uint64_t* empty = full + S;
   uint64_t* xbar = empty + S;   // rank 0: completes when the band sums of ranks 1 .. Z-1 have landed in xred
@@ -732,6 +729,14 @@ __global__ void __launch_bounds__(kThreads, 3)
     if (Z > 1) ptx::cluster_wait_acquire();
   } else {
     const int g = lane >> 2, tig = lane & 3;
+    // scale / bias of the column this thread will store (threads 0 .. 63 of the storing rank): constants, requested now
+    float pre_s = 0.f;
+    T pre_b = DT<T>::from_f(0.f);
+    if ((Z == 1 || z == 0) && threadIdx.x < BN8 && tile * BN8 + static_cast<int>(threadIdx.x) < p.N) {
+      const int n = tile * BN8 + threadIdx.x;
+      pre_s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
+      if (p.bias != nullptr) pre_b = static_cast<const T*>(p.bias)[n];
+    }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float acc2[4] = {0.f, 0.f, 0.f, 0.f};
     int slot = 0, phase = 0;
@@ -777,44 +782,34 @@ __global__ void __launch_bounds__(kThreads, 3)
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = acc[i] + acc2[i];
     const int c0 = 16 * warp + g;
-    if (Z == 1) {
+    if (Z > 1) ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
+    if (Z > 1 && z != 0) {
+      // ranks 1 .. Z-1 push their band sums with st.async onto rank 0's mbarrier and exit; rank 0 adds in rank order
+      const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * MMAX * BN8) * 4u, 0);
+      const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int tok = 2 * tig + (i & 1), n = tile * BN8 + c0 + 8 * (i >> 1);
-        if (tok < p.M && n < p.N) {
-          const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-          static_cast<T*>(p.C)[tok * p.ldc + n] = epilogue<T>(v[i] * s, static_cast<const T*>(p.bias), n);
-        }
+        const int tok = 2 * tig + (i & 1);
+        if (tok < p.M)
+          ptx::st_async_cluster_f32(remote + static_cast<uint32_t>(tok * BN8 + c0 + 8 * (i >> 1)) * 4u, v[i], rbar);
       }
     } else {
-      // ranks 1 .. Z-1 push their band sums with st.async onto rank 0's mbarrier and exit; rank 0 adds in rank order
-      ptx::cluster_wait_acquire();            // every CTA of the cluster runs (phase A)
-      if (z != 0) {
-        const uint32_t remote = ptx::mapa_rank(ptx::smem_u32(xred) + static_cast<uint32_t>(z * MMAX * BN8) * 4u, 0);
-        const uint32_t rbar = ptx::mapa_rank(ptx::smem_u32(xbar), 0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int tok = 2 * tig + (i & 1);
-          if (tok < p.M)
-            ptx::st_async_cluster_f32(remote + static_cast<uint32_t>(tok * BN8 + c0 + 8 * (i >> 1)) * 4u, v[i], rbar);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int tok = 2 * tig + (i & 1);
-          if (tok < p.M) xred[tok * BN8 + c0 + 8 * (i >> 1)] = v[i];
-        }
-        ptx::named_bar_sync(1, CW * 32);
-        if (threadIdx.x < BN8) {
-          ptx::mbar_wait(xbar, 0);
-          const int t = threadIdx.x, n = tile * BN8 + t;
-          if (n < p.N) {
-            const float s = DT<T>::to_f(static_cast<const T*>(p.scale)[n]);
-            for (int m = 0; m < p.M; ++m) {
-              float a = 0.f;
-              for (int zz = 0; zz < Z; ++zz) a += xred[(zz * MMAX + m) * BN8 + t];       // rank order: deterministic
-              static_cast<T*>(p.C)[m * p.ldc + n] = epilogue<T>(a * s, static_cast<const T*>(p.bias), n);
-            }
+      for (int i = 0; i < 4; ++i) {
+        const int tok = 2 * tig + (i & 1);
+        if (tok < p.M) xred[tok * BN8 + c0 + 8 * (i >> 1)] = v[i];
+      }
+      ptx::named_bar_sync(1, CW * 32);
+      if (threadIdx.x < BN8) {
+        if (Z > 1) ptx::mbar_wait(xbar, 0);
+        const int t = threadIdx.x, n = tile * BN8 + t;
+        if (n < p.N) {
+          for (int m = 0; m < p.M; ++m) {
+            float a = 0.f;
+            for (int zz = 0; zz < Z; ++zz) a += xred[(zz * MMAX + m) * BN8 + t];       // rank order: deterministic
+            T val = DT<T>::from_f(a * pre_s);
+            if (p.bias != nullptr) val = DT<T>::from_f(DT<T>::to_f(val) + DT<T>::to_f(pre_b));
+            static_cast<T*>(p.C)[m * p.ldc + n] = val;
           }
         }
       }
@@ -858,7 +853,7 @@ int launch(const GemmArgs& a) {
   prm.Z = Z;
   prm.S = stages;
   const size_t smem = 1024 + static_cast<size_t>(stages) * (W_BYTES + AX_BYTES) +
-                      (Z > 1 ? static_cast<size_t>(Z) * MMAX * BN8 * 4 : 0) + 16 * stages + 48;
+                      static_cast<size_t>(Z) * MMAX * BN8 * 4 + 16 * stages + 48;
   auto kern = w8_gemv_mx_kernel<T>;
   static size_t configured[64] = {0};
   int dev = 0;

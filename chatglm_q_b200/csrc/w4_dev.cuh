@@ -82,6 +82,13 @@ __device__ __forceinline__ uint4 ldnc128(const void* p) {
                : "l"(p));
   return v;
 }
+// one 16-bit element written by the previous kernel of the chain: read past L1
+template <typename T>
+__device__ __forceinline__ T ldcg_t(const T* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return *reinterpret_cast<T*>(&v);
+}
 template <typename T>
 __device__ __forceinline__ float sumsq8(const uint4& v) {
   const T* h = reinterpret_cast<const T*>(&v);
