@@ -56,6 +56,16 @@ def test_abi_argument_errors_without_gpu():
     assert lib.cgq_top_p_sample(P, 200000, 0, 10, 0.8, 1.0, None, None, P, P, None) == -1
     assert lib.cgq_top_p_sample(P, 1000, 0, 10, 0.8, 1.0, None, P, None, None, None) == -1
     assert b"variates" in lib.cgq_last_error()
+    # backward: group != 32, output row shorter than K, dtype code; the decode-arithmetic / simple-kernel switches
+    # are pure host state
+    assert lib.cgq_w4a16_grad_a(P, 16, P, P, P, 64, 2, 16, 64, 16, 0, None) == -1 and b"group" in lib.cgq_last_error()
+    assert lib.cgq_w4a16_grad_a(P, 16, P, P, P, 32, 2, 16, 64, 32, 0, None) == -1
+    assert lib.cgq_w8a16_grad_a(P, 16, P, P, P, 64, 2, 16, 64, 9, None) == -2
+    prev = lib.cgq_set_decode_arith(_lib.ARITH_SUBNORMAL)
+    assert lib.cgq_set_decode_arith(-1) == _lib.ARITH_SUBNORMAL          # query only
+    assert lib.cgq_set_decode_arith(prev) == _lib.ARITH_SUBNORMAL and lib.cgq_set_decode_arith(-1) == prev
+    was = lib.cgq_forbid_simple(1)
+    assert lib.cgq_forbid_simple(was) == 1 and isinstance(lib.cgq_simple_fallback_count(), int)
 
 
 def test_product_never_imports_oracle():
